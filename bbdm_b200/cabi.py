@@ -1,0 +1,243 @@
+"""ctypes binding of include/bbdm_b200.h (the C-ABI drop-in boundary).
+
+Loading fails LOUDLY: if ``libbbdm_b200.so`` is missing the product path raises -- there is no
+eager/PyTorch fallback for the kernels.  ``python -m bbdm_b200.build`` (or
+``__graft_entry__.build()``) compiles it in-tree for sm_100a.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbbdm_b200.so")
+
+ABI_VERSION = 1
+OBJ = {"grad": 0, "noise": 1, "ysubx": 2}
+RESAMPLE_NONE, RESAMPLE_UP2, RESAMPLE_DOWN2 = 0, 1, 2
+RES_NONE, RES_SAME, RES_UP2, RES_DOWN2 = 0, 1, 2, 3
+GN_MAX_SLICES = 64
+
+# every symbol include/bbdm_b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "bbdm_abi_version", "bbdm_last_error", "bbdm_device_info", "bbdm_check_device_fault",
+    "bbdm_bridge_q_sample", "bbdm_bridge_p_sample", "bbdm_nchw_to_nhwc_cat", "bbdm_nhwc_to_nchw",
+    "bbdm_gather_rows", "bbdm_linear_f32", "bbdm_gn_stats", "bbdm_prep_operand",
+    "bbdm_pack_weight_split", "bbdm_pack_weight_f32", "bbdm_conv_umma", "bbdm_conv_direct",
+    "bbdm_attention",
+]
+
+
+class PSampleCoef(C.Structure):
+    _fields_ = [("m_t", C.c_float), ("one_minus_m_t", C.c_float), ("sqrt_var_t", C.c_float),
+                ("m_nt", C.c_float), ("one_minus_m_nt", C.c_float), ("c_xt", C.c_float),
+                ("sigma_t", C.c_float)]
+
+
+class PrepArgs(C.Structure):
+    _fields_ = [("src1", C.c_void_p), ("c1", C.c_int), ("src2", C.c_void_p), ("c2", C.c_int),
+                ("B", C.c_int), ("Hs", C.c_int), ("Ws", C.c_int), ("groups", C.c_int),
+                ("mean", C.c_void_p), ("rstd", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("film_scale", C.c_void_p), ("film_shift", C.c_void_p), ("film_stride", C.c_int64),
+                ("silu", C.c_int), ("resample", C.c_int),
+                ("act_f32", C.c_void_p), ("act_hi", C.c_void_p), ("act_lo", C.c_void_p),
+                ("raw_f32", C.c_void_p), ("raw_hi", C.c_void_p), ("raw_lo", C.c_void_p)]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("Cin", C.c_int), ("Cout", C.c_int), ("taps", C.c_int),
+                ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p),
+                ("bias", C.c_void_p),
+                ("Cin2", C.c_int),
+                ("a2_hi", C.c_void_p), ("a2_lo", C.c_void_p), ("w2_hi", C.c_void_p), ("w2_lo", C.c_void_p),
+                ("bias2", C.c_void_p),
+                ("residual", C.c_void_p), ("res_mode", C.c_int),
+                ("out", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
+                ("passes", C.c_int)]
+
+
+class BbdmError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """dlopen the C-ABI library and declare prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BbdmError(
+            f"{LIB_PATH} not found: build the sm_100a kernels first (python -m bbdm_b200.build). "
+            "bbdm_b200 has no PyTorch/CPU fallback for its kernels.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i, i64, f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    lib.bbdm_abi_version.restype = i
+    lib.bbdm_last_error.restype = C.c_char_p
+    lib.bbdm_device_info.argtypes = [C.POINTER(i)] * 3
+    lib.bbdm_check_device_fault.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    lib.bbdm_bridge_q_sample.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp, vp, i, i64, vp]
+    lib.bbdm_bridge_p_sample.argtypes = [vp, vp, vp, vp, PSampleCoef, i, i, i, vp, vp, i64, vp]
+    lib.bbdm_nchw_to_nhwc_cat.argtypes = [vp, i, vp, i, i, i, i, vp, vp]
+    lib.bbdm_nhwc_to_nchw.argtypes = [vp, i, i, i, i, vp, vp]
+    lib.bbdm_gather_rows.argtypes = [vp, i, i, vp, i, vp, vp]
+    lib.bbdm_linear_f32.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp]
+    lib.bbdm_gn_stats.argtypes = [vp, i, vp, i, i, i, i, i, f, vp, vp, vp, vp]
+    lib.bbdm_prep_operand.argtypes = [C.POINTER(PrepArgs), vp]
+    lib.bbdm_pack_weight_split.argtypes = [vp, i, i, i, vp, vp, vp]
+    lib.bbdm_pack_weight_f32.argtypes = [vp, i, i, i, vp, vp]
+    lib.bbdm_conv_umma.argtypes = [C.POINTER(ConvArgs), vp]
+    lib.bbdm_conv_direct.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
+    lib.bbdm_attention.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp]
+    for s in SYMBOLS:
+        fn = getattr(lib, s)
+        if s not in ("bbdm_last_error",):
+            fn.restype = i
+    if lib.bbdm_abi_version() != ABI_VERSION:
+        raise BbdmError(f"libbbdm_b200.so ABI {lib.bbdm_abi_version()} != binding ABI {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise BbdmError(f"bbdm_b200 C-ABI call failed ({rc}): {load().bbdm_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# launch counter: every successful C-ABI compute call == >=1 kernel launch of OUR kernels
+LAUNCHES = {"n": 0}
+
+
+def _req(t, dtype=torch.float32):
+    assert t.is_cuda and t.is_contiguous() and t.dtype == dtype, (t.device, t.dtype, t.is_contiguous())
+    return t
+
+
+class CudaBackend:
+    """The one product backend: each method is one C-ABI entry point on torch's current stream.
+    (tests/ substitute an oracle-backed emulation with the same method set to check the host
+    logic on CPU; the product never does.)"""
+
+    name = "sm_100a"
+
+    def __init__(self):
+        self.lib = load()
+
+    # -- memory ------------------------------------------------------------------------------
+    def empty(self, shape, dtype, device):
+        return torch.empty(shape, dtype=dtype, device=device)
+
+    # -- bridge --------------------------------------------------------------------------------
+    def q_sample(self, x0, y, noise, t, m_t, var_t, objective, xt_out, obj_out):
+        B = x0.shape[0]
+        n = x0.numel() // B
+        for z in (x0, y, noise, m_t, var_t, xt_out, obj_out):
+            _req(z)
+        _req(t, torch.int64)
+        check(self.lib.bbdm_bridge_q_sample(ptr(x0), ptr(y), ptr(noise), ptr(t), ptr(m_t), ptr(var_t),
+                                            m_t.numel(), OBJ[objective], ptr(xt_out), ptr(obj_out), B, n,
+                                            stream()))
+        LAUNCHES["n"] += 1
+
+    def p_sample(self, x_t, y, eps, noise, coef, objective, clip, is_last, x_out, x0_out):
+        for z in (x_t, y, eps, x_out):
+            _req(z)
+        c = PSampleCoef(*[float(v) for v in coef])
+        check(self.lib.bbdm_bridge_p_sample(ptr(x_t), ptr(y), ptr(eps), ptr(noise), c, OBJ[objective],
+                                            int(clip), int(is_last), ptr(x_out), ptr(x0_out), x_t.numel(),
+                                            stream()))
+        LAUNCHES["n"] += 1
+
+    # -- layout / dense ----------------------------------------------------------------------
+    def nchw_to_nhwc_cat(self, x, ctx, out):
+        B, c1, H, W = x.shape
+        c2 = 0 if ctx is None else ctx.shape[1]
+        check(self.lib.bbdm_nchw_to_nhwc_cat(ptr(_req(x)), c1, ptr(ctx), c2, B, H, W, ptr(_req(out)), stream()))
+        LAUNCHES["n"] += 1
+
+    def nhwc_to_nchw(self, src, out):
+        B, H, W, Cc = src.shape
+        check(self.lib.bbdm_nhwc_to_nchw(ptr(_req(src)), B, H, W, Cc, ptr(_req(out)), stream()))
+        LAUNCHES["n"] += 1
+
+    def gather_rows(self, table, idx, out):
+        check(self.lib.bbdm_gather_rows(ptr(_req(table)), table.shape[0], table.shape[1],
+                                        ptr(_req(idx, torch.int64)), idx.numel(), ptr(_req(out)), stream()))
+        LAUNCHES["n"] += 1
+
+    def linear(self, x, w, bias, out, act_in=False, act_out=False):
+        B, K = x.shape
+        N = w.shape[0]
+        check(self.lib.bbdm_linear_f32(ptr(_req(x)), ptr(_req(w)), ptr(bias), ptr(_req(out)), B, K, N,
+                                       int(act_in), int(act_out), stream()))
+        LAUNCHES["n"] += (B + 7) // 8
+
+    # -- group norm / prep ---------------------------------------------------------------------
+    def gn_stats(self, src1, src2, groups, eps, mean, rstd, workspace):
+        B, H, W, c1 = src1.shape
+        c2 = 0 if src2 is None else src2.shape[3]
+        check(self.lib.bbdm_gn_stats(ptr(_req(src1)), c1, ptr(src2), c2, B, H, W, groups, eps,
+                                     ptr(_req(mean)), ptr(_req(rstd)), ptr(workspace), stream()))
+        LAUNCHES["n"] += 2
+
+    def prep(self, src1, src2, *, groups=32, mean=None, rstd=None, gamma=None, beta=None,
+             film_scale=None, film_shift=None, film_stride=0, silu=True, resample=RESAMPLE_NONE,
+             act_f32=None, act_hi=None, act_lo=None, raw_f32=None, raw_hi=None, raw_lo=None):
+        B, Hs, Ws, c1 = src1.shape
+        a = PrepArgs(ptr(_req(src1)), c1, ptr(src2), 0 if src2 is None else src2.shape[3], B, Hs, Ws, groups,
+                     ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(film_scale), ptr(film_shift),
+                     film_stride, int(silu), resample, ptr(act_f32), ptr(act_hi), ptr(act_lo),
+                     ptr(raw_f32), ptr(raw_hi), ptr(raw_lo))
+        check(self.lib.bbdm_prep_operand(C.byref(a), stream()))
+        LAUNCHES["n"] += 1
+
+    # -- convolutions --------------------------------------------------------------------------
+    def pack_weight_split(self, w, hi, lo):
+        Cout, Cin, k = w.shape[0], w.shape[1], (w.shape[2] if w.dim() > 2 else 1)
+        check(self.lib.bbdm_pack_weight_split(ptr(_req(w)), Cout, Cin, k, ptr(hi), ptr(lo), stream()))
+        LAUNCHES["n"] += 1
+
+    def pack_weight_f32(self, w, out):
+        Cout, Cin, k = w.shape[0], w.shape[1], (w.shape[2] if w.dim() > 2 else 1)
+        check(self.lib.bbdm_pack_weight_f32(ptr(_req(w)), Cout, Cin, k, ptr(_req(out)), stream()))
+        LAUNCHES["n"] += 1
+
+    def conv_umma(self, *, B, H, W, Cin, Cout, taps, a_hi, a_lo, w_hi, w_lo, bias=None, Cin2=0,
+                  a2_hi=None, a2_lo=None, w2_hi=None, w2_lo=None, bias2=None, residual=None,
+                  res_mode=RES_NONE, out=None, out_hi=None, out_lo=None, passes=3):
+        a = ConvArgs(B, H, W, Cin, Cout, taps, ptr(a_hi), ptr(a_lo), ptr(w_hi), ptr(w_lo), ptr(bias),
+                     Cin2, ptr(a2_hi), ptr(a2_lo), ptr(w2_hi), ptr(w2_lo), ptr(bias2),
+                     ptr(residual), res_mode, ptr(out), ptr(out_hi), ptr(out_lo), passes)
+        check(self.lib.bbdm_conv_umma(C.byref(a), stream()))
+        LAUNCHES["n"] += 1
+
+    def conv_direct(self, src, w_packed, bias, residual, out, Cout, k, stride=1):
+        B, H, W, Cin = src.shape
+        check(self.lib.bbdm_conv_direct(ptr(_req(src)), ptr(_req(w_packed)), ptr(bias), ptr(residual),
+                                        ptr(_req(out)), B, H, W, Cin, Cout, k, stride, stream()))
+        LAUNCHES["n"] += 1
+
+    # -- attention -------------------------------------------------------------------------------
+    def attention(self, qkv, heads, order, out_f32=None, out_hi=None, out_lo=None):
+        B, T, C3 = qkv.shape
+        check(self.lib.bbdm_attention(ptr(_req(qkv)), B, T, C3 // 3, heads, order, ptr(out_f32),
+                                      ptr(out_hi), ptr(out_lo), stream()))
+        LAUNCHES["n"] += 1
+
+    def check_fault(self):
+        w = C.c_ulonglong(0)
+        check(self.lib.bbdm_check_device_fault(stream(), C.byref(w)))

@@ -1,0 +1,82 @@
+// Shared helpers for the bbdm_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/bbdm_b200.h"
+
+namespace bbdm {
+
+// ---- host-side error plumbing ------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+// device fault word (mbarrier wait timeouts etc.); lives in cabi.cu
+unsigned long long* device_fault_ptr();
+
+#define BBDM_CUDA_CHECK(expr)                                                   \
+  do {                                                                          \
+    cudaError_t _e = (expr);                                                    \
+    if (_e != cudaSuccess) return ::bbdm::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define BBDM_REQUIRE(cond, ...)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::bbdm::set_error(__VA_ARGS__);      \
+      return BBDM_E_INVALID;               \
+    }                                      \
+  } while (0)
+
+#define BBDM_LAUNCH_CHECK() BBDM_CUDA_CHECK(cudaGetLastError())
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---- device helpers ----------------------------------------------------------------------
+__device__ __forceinline__ float silu_f(float x) {
+  // x * sigmoid(x) = x / (1 + exp(-x)); expf (not __expf) keeps ~1 ulp like torch's CPU path
+  return x / (1.0f + expf(-x));
+}
+
+// hi = bf16(x) (round-to-nearest-even), lo = bf16(x - hi)
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// split 4 floats -> two uint2 (4 bf16 each)
+__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
+  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+  split_bf16(v.x, h0, l0);
+  split_bf16(v.y, h1, l1);
+  split_bf16(v.z, h2, l2);
+  split_bf16(v.w, h3, l3);
+  hi = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+  lo = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st_f4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+}  // namespace bbdm

@@ -1,0 +1,510 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+//   out[pixel, co] = sum_{tap, ci} A[pixel + tap, ci] * W[tap, co, ci]  (+ fused 1x1 operand)
+//                    + bias (+ bias2) (+ residual)
+//
+//   * M tile = 128 output pixels = a (TW x TH x TB) box of the NHWC tensor; N tile = BN couts;
+//     K block = 64 input channels of one filter tap.
+//   * Operands are split-bf16 planes (hi, lo).  passes=3 issues A_hi.W_hi + A_lo.W_hi + A_hi.W_lo
+//     into the same TMEM accumulator (fp32-class accuracy); passes=1 issues A_hi.W_hi only.
+//   * TMA (cp.async.bulk.tensor, 4-D tiled map, SWIZZLE_128B) stages the shifted pixel box of a
+//     tap straight from the activation tensor; out-of-image coordinates are zero-filled by the
+//     TMA unit, which IS the conv padding -- no im2col buffer, no halo logic.
+//   * Warp-specialised persistent CTA: warp0 = TMA producer, warp1 = tcgen05.mma issuer (one
+//     elected lane) + TMEM owner, warps2-5 = epilogue (TMEM -> registers -> bias/residual ->
+//     global).  Two TMEM accumulator buffers so the epilogue of tile i overlaps the mainloop of
+//     tile i+1.
+//   * Every mbarrier wait has a clock-based watchdog: on expiry a device fault word is set and
+//     the CTA drains without deadlocking the GPU (bbdm_check_device_fault reports it).
+#include "common.cuh"
+#include <cuda.h>
+
+namespace bbdm {
+
+constexpr int UM_BM = 128;       // pixels per tile (UMMA M)
+constexpr int UM_BK = 64;        // bf16 per K block = 128 B rows (SWIZZLE_128B)
+constexpr int UM_THREADS = 192;  // 6 warps
+constexpr uint32_t UM_A_BYTES = UM_BM * UM_BK * 2;  // 16 KiB per plane per stage
+
+// ---------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait.  *abort_flag (shared) is sticky: once any wait in the CTA expired, the rest
+// return at once so the kernel terminates.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag,
+                                          unsigned long long* fault, unsigned long long code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*abort_flag) return;
+    if (clock64() - t0 > 1000000000ll) {   // ~0.5 s
+      *abort_flag = 1;
+      atomicExch(fault, code);
+      return;
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// SWIZZLE_128B, K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 = 1024 B
+//   (8 rows x 128 B) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct ConvParams {
+  int B, H, W, Cout;
+  int TW, TH, TB, tiles_w, tiles_h, tiles_b, n_tiles;
+  int kb_per_tap;   // Cin / 64
+  int K1;           // taps * Cin/64
+  int K2;           // Cin2 / 64
+  int taps;
+  int passes;
+  const float* bias; const float* bias2;
+  const float* residual; int res_mode;
+  float* out; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+  unsigned long long* fault;
+};
+
+template <int BN>
+struct UmmaCfg {
+  static constexpr uint32_t W_BYTES = BN * UM_BK * 2;
+  static constexpr uint32_t STAGE3 = 2 * UM_A_BYTES + 2 * W_BYTES;  // hi+lo planes
+  static constexpr uint32_t STAGE1 = UM_A_BYTES + W_BYTES;
+  static constexpr uint32_t SMEM_BUDGET = 200 * 1024;
+  static constexpr int STAGES3 = (SMEM_BUDGET / STAGE3) > 6 ? 6 : (SMEM_BUDGET / STAGE3);
+  static constexpr int STAGES1 = (SMEM_BUDGET / STAGE1) > 8 ? 8 : (SMEM_BUDGET / STAGE1);
+  static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // power of two for BN in {64,128,256}
+};
+
+template <int BN, int PASSES>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                 const __grid_constant__ CUtensorMap map_a2_hi, const __grid_constant__ CUtensorMap map_a2_lo,
+                 const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
+                 const ConvParams p) {
+  using Cfg = UmmaCfg<BN>;
+  constexpr int STAGES = PASSES == 3 ? Cfg::STAGES3 : Cfg::STAGES1;
+  constexpr uint32_t STAGE_BYTES = PASSES == 3 ? Cfg::STAGE3 : Cfg::STAGE1;
+  constexpr uint32_t OFF_ALO = UM_A_BYTES;
+  constexpr uint32_t OFF_WHI = PASSES == 3 ? 2 * UM_A_BYTES : UM_A_BYTES;
+  constexpr uint32_t OFF_WLO = OFF_WHI + Cfg::W_BYTES;
+  static_assert(STAGES >= 2, "need at least a double buffer");
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * 8 + 4];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int abort_s;
+
+  const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = smem_u32(&bars[0]);        // [STAGES]
+  const uint32_t bar_empty = smem_u32(&bars[8]);       // [STAGES]
+  const uint32_t bar_tfull = smem_u32(&bars[16]);      // [2]
+  const uint32_t bar_tempty = smem_u32(&bars[18]);     // [2]
+  volatile int* abort_flag = &abort_s;
+
+  if (threadIdx.x == 0) {
+    abort_s = 0;
+    for (int i = 0; i < STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(&tmem_base_s)), "n"(Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int n_blocks = p.Cout / BN;
+  const int total_tiles = p.n_tiles * n_blocks;
+  const int KB = p.K1 + p.K2;
+
+  if (warp == 0) {
+    // ================================ TMA producer ==========================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nb = tile % n_blocks;
+        int mt = tile / n_blocks;
+        const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+        const int th = mt % p.tiles_h;
+        const int tb = mt / p.tiles_h;
+        const int w0 = tw * p.TW, h0 = th * p.TH, b0 = tb * p.TB, n0 = nb * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1, abort_flag, p.fault, 0xE0000000ull | (unsigned)kb);
+          const uint32_t sbase = tiles_base + stage * STAGE_BYTES;
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_expect_tx(full, STAGE_BYTES);
+          if (kb < p.K1) {
+            const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
+            int dy = 0, dx = 0;
+            if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+            tma_load_4d(sbase, &map_a_hi, full, cb * UM_BK, w0 + dx, h0 + dy, b0);
+            if (PASSES == 3) tma_load_4d(sbase + OFF_ALO, &map_a_lo, full, cb * UM_BK, w0 + dx, h0 + dy, b0);
+            tma_load_3d(sbase + OFF_WHI, &map_w_hi, full, cb * UM_BK, n0, tap);
+            if (PASSES == 3) tma_load_3d(sbase + OFF_WLO, &map_w_lo, full, cb * UM_BK, n0, tap);
+          } else {
+            const int cb = kb - p.K1;
+            tma_load_4d(sbase, &map_a2_hi, full, cb * UM_BK, w0, h0, b0);
+            if (PASSES == 3) tma_load_4d(sbase + OFF_ALO, &map_a2_lo, full, cb * UM_BK, w0, h0, b0);
+            tma_load_3d(sbase + OFF_WHI, &map_w2_hi, full, cb * UM_BK, n0, 0);
+            if (PASSES == 3) tma_load_3d(sbase + OFF_WLO, &map_w2_lo, full, cb * UM_BK, n0, 0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer ============================================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
+      constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)(UM_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, abort_flag, p.fault, 0xA0000000ull | (unsigned)tile);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase, abort_flag, p.fault, 0xF0000000ull | (unsigned)kb);
+          tc_fence_after();
+          const uint32_t sbase = tiles_base + stage * STAGE_BYTES;
+          const uint64_t da_hi = make_sw128_desc(sbase);
+          const uint64_t da_lo = make_sw128_desc(sbase + OFF_ALO);
+          const uint64_t db_hi = make_sw128_desc(sbase + OFF_WHI);
+          const uint64_t db_lo = make_sw128_desc(sbase + OFF_WLO);
+#pragma unroll
+          for (int k = 0; k < UM_BK / 16; ++k) {
+            const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 B per UMMA_K inside the swizzle atom
+            const uint32_t first = (kb | k) ? 1u : 0u;
+            if (PASSES == 3) {
+              tc_mma_bf16(d_tmem, da_lo + ko, db_hi + ko, IDESC, first);
+              tc_mma_bf16(d_tmem, da_hi + ko, db_lo + ko, IDESC, 1u);
+              tc_mma_bf16(d_tmem, da_hi + ko, db_hi + ko, IDESC, 1u);
+            } else {
+              tc_mma_bf16(d_tmem, da_hi + ko, db_hi + ko, IDESC, first);
+            }
+          }
+          tc_commit(bar_empty + 8 * stage);          // frees the smem slot when these MMAs retire
+          if (kb == KB - 1) tc_commit(bar_tfull + 8 * acc);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ epilogue (4 warps) ====================================
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;             // tile row == TMEM lane
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nb = tile % n_blocks;
+      int mt = tile / n_blocks;
+      const int tw = mt % p.tiles_w; mt /= p.tiles_w;
+      const int th = mt % p.tiles_h;
+      const int tb = mt / p.tiles_h;
+      const int ww = tw * p.TW + row % p.TW;
+      const int hh = th * p.TH + (row / p.TW) % p.TH;
+      const int bb = tb * p.TB + row / (p.TW * p.TH);
+      const bool valid = ww < p.W && hh < p.H && bb < p.B;
+      const int64_t pix = ((int64_t)bb * p.H + hh) * p.W + ww;
+      const int n0 = nb * BN;
+
+      mbar_wait(bar_tfull + 8 * acc, acc_phase, abort_flag, p.fault, 0xD0000000ull | (unsigned)tile);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32];
+        tc_ld32(t_addr + ch * 32, v);
+        tc_wait_ld();
+        if (valid) {
+          const int nc = n0 + ch * 32;
+          float r[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = ld_f4(p.bias + nc + j);
+              r[j] += bv.x; r[j + 1] += bv.y; r[j + 2] += bv.z; r[j + 3] += bv.w;
+            }
+          }
+          if (p.bias2) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = ld_f4(p.bias2 + nc + j);
+              r[j] += bv.x; r[j + 1] += bv.y; r[j + 2] += bv.z; r[j + 3] += bv.w;
+            }
+          }
+          if (p.res_mode == BBDM_RES_SAME) {
+            const float* rp = p.residual + pix * p.Cout + nc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = ld_f4(rp + j);
+              r[j] += t.x; r[j + 1] += t.y; r[j + 2] += t.z; r[j + 3] += t.w;
+            }
+          } else if (p.res_mode == BBDM_RES_UP2) {
+            const float* rp = p.residual + (((int64_t)bb * (p.H >> 1) + (hh >> 1)) * (p.W >> 1) + (ww >> 1)) * p.Cout + nc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = ld_f4(rp + j);
+              r[j] += t.x; r[j + 1] += t.y; r[j + 2] += t.z; r[j + 3] += t.w;
+            }
+          } else if (p.res_mode == BBDM_RES_DOWN2) {
+            const int64_t W2 = (int64_t)p.W * 2;
+            const float* rp = p.residual + (((int64_t)bb * p.H * 2 + hh * 2) * W2 + ww * 2) * p.Cout + nc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t0 = ld_f4(rp + j), t1 = ld_f4(rp + p.Cout + j);
+              const float4 t2 = ld_f4(rp + W2 * p.Cout + j), t3 = ld_f4(rp + (W2 + 1) * p.Cout + j);
+              r[j] += 0.25f * (((t0.x + t1.x) + t2.x) + t3.x);
+              r[j + 1] += 0.25f * (((t0.y + t1.y) + t2.y) + t3.y);
+              r[j + 2] += 0.25f * (((t0.z + t1.z) + t2.z) + t3.z);
+              r[j + 3] += 0.25f * (((t0.w + t1.w) + t2.w) + t3.w);
+            }
+          }
+          if (p.out) {
+            float* op = p.out + pix * p.Cout + nc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) st_f4(op + j, make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]));
+          }
+          if (p.out_hi) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              uint2 h, l;
+              split4(make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]), h, l);
+              *reinterpret_cast<uint2*>(p.out_hi + pix * p.Cout + nc + j) = h;
+              *reinterpret_cast<uint2*>(p.out_lo + pix * p.Cout + nc + j) = l;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// bf16 NHWC activation [B,H,W,C] -> 4-D map (C, W, H, B), box (64, TW, TH, TB), SWIZZLE_128B
+static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int TW, int TH, int TB) {
+  EncodeTiledFn enc = get_encode();
+  BBDM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)UM_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BBDM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: %d (B=%d H=%d W=%d C=%d box=%dx%dx%d)",
+               (int)r, B, H, W, C, TW, TH, TB);
+  return BBDM_OK;
+}
+
+// bf16 weights [taps][Cout][Cin] -> 3-D map (Cin, Cout, taps), box (64, BN, 1)
+static int make_w_map(CUtensorMap* m, const void* ptr, int taps, int Cout, int Cin, int BN) {
+  EncodeTiledFn enc = get_encode();
+  BBDM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+  cuuint32_t box[3] = {(cuuint32_t)UM_BK, (cuuint32_t)BN, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BBDM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed: %d (taps=%d Cout=%d Cin=%d BN=%d)", (int)r,
+               taps, Cout, Cin, BN);
+  return BBDM_OK;
+}
+
+static int pow2_floor(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
+static int pow2_ceil(int x) { int p = 1; while (p < x) p *= 2; return p; }
+
+template <int BN, int PASSES>
+static int launch_conv(const CUtensorMap* maps, const ConvParams& p, int grid, cudaStream_t s) {
+  using Cfg = UmmaCfg<BN>;
+  constexpr int STAGES = PASSES == 3 ? Cfg::STAGES3 : Cfg::STAGES1;
+  constexpr uint32_t STAGE_BYTES = PASSES == 3 ? Cfg::STAGE3 : Cfg::STAGE1;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+  static bool configured = false;
+  if (!configured) {
+    BBDM_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  conv_umma_kernel<BN, PASSES><<<grid, UM_THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
+                                                              maps[6], maps[7], p);
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
+}  // namespace bbdm
+
+using namespace bbdm;
+
+extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
+  BBDM_REQUIRE(a != nullptr, "conv_umma: null args");
+  BBDM_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0, "conv_umma: bad spatial shape");
+  BBDM_REQUIRE(a->taps == 1 || a->taps == 9, "conv_umma: taps must be 1 or 9 (got %d)", a->taps);
+  BBDM_REQUIRE(a->Cin > 0 && a->Cin % 64 == 0, "conv_umma: Cin %% 64 != 0 (Cin=%d)", a->Cin);
+  BBDM_REQUIRE(a->Cout > 0 && a->Cout % 64 == 0, "conv_umma: Cout %% 64 != 0 (Cout=%d)", a->Cout);
+  BBDM_REQUIRE(a->Cin2 >= 0 && a->Cin2 % 64 == 0, "conv_umma: Cin2 %% 64 != 0 (Cin2=%d)", a->Cin2);
+  BBDM_REQUIRE(a->passes == 1 || a->passes == 3, "conv_umma: passes must be 1 or 3");
+  BBDM_REQUIRE(a->a_hi && a->w_hi && (a->passes == 1 || (a->a_lo && a->w_lo)), "conv_umma: missing operand plane");
+  if (a->Cin2) BBDM_REQUIRE(a->a2_hi && a->w2_hi && (a->passes == 1 || (a->a2_lo && a->w2_lo)), "conv_umma: missing 1x1 operand plane");
+  BBDM_REQUIRE(a->out || (a->out_hi && a->out_lo), "conv_umma: no output");
+  BBDM_REQUIRE((a->out_hi == nullptr) == (a->out_lo == nullptr), "conv_umma: out hi/lo must come in pairs");
+  BBDM_REQUIRE(a->res_mode >= 0 && a->res_mode <= 3 && (a->res_mode == 0 || a->residual), "conv_umma: bad residual");
+  if (a->res_mode == BBDM_RES_UP2) BBDM_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0, "conv_umma: RES_UP2 needs even H, W");
+  BBDM_REQUIRE(a->W >= 4, "conv_umma: W < 4 not supported (use conv_direct)");
+
+  ConvParams p;
+  p.B = a->B; p.H = a->H; p.W = a->W; p.Cout = a->Cout;
+  p.TW = pow2_floor(a->W) < 16 ? pow2_floor(a->W) : 16;
+  int th = pow2_ceil(a->H);
+  p.TH = th < UM_BM / p.TW ? th : UM_BM / p.TW;
+  p.TB = UM_BM / (p.TW * p.TH);
+  p.tiles_w = (a->W + p.TW - 1) / p.TW;
+  p.tiles_h = (a->H + p.TH - 1) / p.TH;
+  p.tiles_b = (a->B + p.TB - 1) / p.TB;
+  p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+  p.kb_per_tap = a->Cin / 64;
+  p.K1 = a->taps * p.kb_per_tap;
+  p.K2 = a->Cin2 / 64;
+  p.taps = a->taps;
+  p.passes = a->passes;
+  p.bias = a->bias; p.bias2 = a->Cin2 ? a->bias2 : nullptr;
+  p.residual = a->residual; p.res_mode = a->res_mode;
+  p.out = a->out; p.out_hi = (__nv_bfloat16*)a->out_hi; p.out_lo = (__nv_bfloat16*)a->out_lo;
+  p.fault = device_fault_ptr();
+  BBDM_REQUIRE(p.fault != nullptr, "conv_umma: device fault word unavailable");
+
+  const int BN = (a->Cout % 256 == 0) ? 256 : (a->Cout % 128 == 0 ? 128 : 64);
+  CUtensorMap maps[8];
+  int rc;
+  if ((rc = make_act_map(&maps[0], a->a_hi, a->B, a->H, a->W, a->Cin, p.TW, p.TH, p.TB))) return rc;
+  if ((rc = make_act_map(&maps[1], a->passes == 3 ? a->a_lo : a->a_hi, a->B, a->H, a->W, a->Cin, p.TW, p.TH, p.TB))) return rc;
+  if ((rc = make_w_map(&maps[2], a->w_hi, a->taps, a->Cout, a->Cin, BN))) return rc;
+  if ((rc = make_w_map(&maps[3], a->passes == 3 ? a->w_lo : a->w_hi, a->taps, a->Cout, a->Cin, BN))) return rc;
+  if (a->Cin2) {
+    if ((rc = make_act_map(&maps[4], a->a2_hi, a->B, a->H, a->W, a->Cin2, p.TW, p.TH, p.TB))) return rc;
+    if ((rc = make_act_map(&maps[5], a->passes == 3 ? a->a2_lo : a->a2_hi, a->B, a->H, a->W, a->Cin2, p.TW, p.TH, p.TB))) return rc;
+    if ((rc = make_w_map(&maps[6], a->w2_hi, 1, a->Cout, a->Cin2, BN))) return rc;
+    if ((rc = make_w_map(&maps[7], a->passes == 3 ? a->w2_lo : a->w2_hi, 1, a->Cout, a->Cin2, BN))) return rc;
+  } else {
+    maps[4] = maps[0]; maps[5] = maps[1]; maps[6] = maps[2]; maps[7] = maps[3];
+  }
+  const int64_t total = (int64_t)p.n_tiles * (a->Cout / BN);
+  BBDM_REQUIRE(total < (1ll << 30), "conv_umma: too many tiles");
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  cudaStream_t s = (cudaStream_t)stream;
+#define BBDM_UL(N)                                                        \
+  (a->passes == 3 ? launch_conv<N, 3>(maps, p, grid, s) : launch_conv<N, 1>(maps, p, grid, s))
+  if (BN == 256) return BBDM_UL(256);
+  if (BN == 128) return BBDM_UL(128);
+  return BBDM_UL(64);
+#undef BBDM_UL
+}

@@ -1,0 +1,305 @@
+// HBM-bound elementwise / layout / small dense kernels of the BBDM hot path.
+//   bridge q_sample / p_sample  (BrownianBridgeModel.py:128-160,171-201)  20-24 B/element
+//   NCHW<->NHWC edge transforms, table gather, small fp32 linear, weight repacking
+#include "common.cuh"
+
+namespace bbdm {
+
+// ------------------------------------------------------------------------------------------
+// q_sample.  One fp32 rounding per reference torch op (no FMA contraction) => bit-exact.
+//   x_t = ((1-m) * x0 + m * y) + s * noise ;  obj(grad) = m * (y - x0) + s * noise
+// ------------------------------------------------------------------------------------------
+template <int OBJ>
+__global__ void __launch_bounds__(256)
+q_sample_kernel(const float4* __restrict__ x0, const float4* __restrict__ y,
+                const float4* __restrict__ nz, const int64_t* __restrict__ t,
+                const float* __restrict__ m_tab, const float* __restrict__ v_tab,
+                float4* __restrict__ xt, float4* __restrict__ obj, int64_t n4_per_sample) {
+  const int b = blockIdx.y;
+  const float m = m_tab[t[b]];
+  const float s = __fsqrt_rn(v_tab[t[b]]);
+  const float om = __fsub_rn(1.0f, m);
+  const int64_t base = (int64_t)b * n4_per_sample;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4_per_sample;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = x0[base + i], c = y[base + i], e = nz[base + i];
+    float4 o, q;
+#define BBDM_Q1(f)                                                                      \
+  {                                                                                     \
+    const float sn = __fmul_rn(s, e.f);                                                 \
+    o.f = __fadd_rn(__fadd_rn(__fmul_rn(om, a.f), __fmul_rn(m, c.f)), sn);              \
+    if (OBJ == BBDM_OBJ_GRAD) q.f = __fadd_rn(__fmul_rn(m, __fsub_rn(c.f, a.f)), sn);   \
+    else if (OBJ == BBDM_OBJ_NOISE) q.f = e.f;                                          \
+    else q.f = __fsub_rn(c.f, a.f);                                                     \
+  }
+    BBDM_Q1(x) BBDM_Q1(y) BBDM_Q1(z) BBDM_Q1(w)
+#undef BBDM_Q1
+    xt[base + i] = o;
+    obj[base + i] = q;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// p_sample update (scalars identical across the batch in sampling).
+// ------------------------------------------------------------------------------------------
+template <int OBJ, bool CLIP, bool LAST>
+__global__ void __launch_bounds__(256)
+p_sample_kernel(const float4* __restrict__ xt, const float4* __restrict__ y,
+                const float4* __restrict__ eps, const float4* __restrict__ nz,
+                BbdmPSampleCoef c, float4* __restrict__ out, float4* __restrict__ x0o, int64_t n4) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 X = xt[i], Y = y[i], E = eps[i];
+    float4 N = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!LAST) N = nz[i];
+    float4 O, R;
+#define BBDM_P1(f)                                                                             \
+  {                                                                                            \
+    float x0;                                                                                  \
+    if (OBJ == BBDM_OBJ_GRAD) x0 = __fsub_rn(X.f, E.f);                                        \
+    else if (OBJ == BBDM_OBJ_NOISE)                                                            \
+      x0 = __fdiv_rn(__fsub_rn(__fsub_rn(X.f, __fmul_rn(c.m_t, Y.f)),                          \
+                               __fmul_rn(c.sqrt_var_t, E.f)), c.one_minus_m_t);                \
+    else x0 = __fsub_rn(Y.f, E.f);                                                             \
+    if (CLIP) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);                                              \
+    R.f = x0;                                                                                  \
+    if (LAST) O.f = x0;                                                                        \
+    else {                                                                                     \
+      const float a = __fadd_rn(__fmul_rn(c.one_minus_m_nt, x0), __fmul_rn(c.m_nt, Y.f));      \
+      const float d = __fsub_rn(__fsub_rn(X.f, __fmul_rn(c.one_minus_m_t, x0)),                \
+                                __fmul_rn(c.m_t, Y.f));                                        \
+      const float mean = __fadd_rn(a, __fmul_rn(c.c_xt, d));                                   \
+      O.f = __fadd_rn(mean, __fmul_rn(c.sigma_t, N.f));                                        \
+    }                                                                                          \
+  }
+    BBDM_P1(x) BBDM_P1(y) BBDM_P1(z) BBDM_P1(w)
+#undef BBDM_P1
+    out[i] = O;
+    if (x0o) x0o[i] = R;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// NCHW (+NCHW ctx) -> NHWC concat.  C is tiny (3..32): one thread per pixel, coalesced reads
+// per channel plane, contiguous C-vector write per pixel.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_cat_kernel(const float* __restrict__ x, int c1, const float* __restrict__ ctx, int c2,
+                        int64_t HW, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int C = c1 + c2;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    float* o = out + ((int64_t)b * HW + p) * C;
+    for (int c = 0; c < c1; ++c) o[c] = x[((int64_t)b * c1 + c) * HW + p];
+    for (int c = 0; c < c2; ++c) o[c1 + c] = ctx[((int64_t)b * c2 + c) * HW + p];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const float* __restrict__ src, int C, int64_t HW, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    const float* s = src + ((int64_t)b * HW + p) * C;
+    for (int c = 0; c < C; ++c) out[((int64_t)b * C + c) * HW + p] = s[c];
+  }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ table, int rows, int width,
+                                   const int64_t* __restrict__ idx, float* __restrict__ out) {
+  const int b = blockIdx.x;
+  int64_t r = idx[b];
+  r = r < 0 ? 0 : (r >= rows ? rows - 1 : r);
+  for (int i = threadIdx.x; i < width; i += blockDim.x) out[(int64_t)b * width + i] = table[r * width + i];
+}
+
+// ------------------------------------------------------------------------------------------
+// Small fp32 linear: one warp per output column n, all B rows (B <= 64 per pass) at once so
+// the weight row is read exactly once (weight-bandwidth bound, 4 B/param).
+// ------------------------------------------------------------------------------------------
+template <int BT>
+__global__ void __launch_bounds__(256)
+linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                  const float* __restrict__ bias, float* __restrict__ out, int B, int K, int N,
+                  int act_in, int act_out, int b0) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const float* wr = w + (int64_t)warp * K;
+  float acc[BT];
+#pragma unroll
+  for (int b = 0; b < BT; ++b) acc[b] = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = wr[k];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      if (b0 + b < B) {
+        float xv = x[(int64_t)(b0 + b) * K + k];
+        if (act_in) xv = silu_f(xv);
+        acc[b] = fmaf(xv, wv, acc[b]);
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < BT; ++b) {
+    const float s = warp_sum(acc[b]);
+    if (lane == 0 && b0 + b < B) {
+      float v = s + (bias ? bias[warp] : 0.f);
+      if (act_out) v = silu_f(v);
+      out[(int64_t)(b0 + b) * N + warp] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight repacking: OIHW fp32 -> [tap][Cout][Cin] split bf16 / [tap][Cin][Cout] fp32
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_weight_split_kernel(const float* __restrict__ w, int Cout, int Cin, int kk,
+                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int64_t n = (int64_t)kk * Cout * Cin;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const int co = (int)((i / Cin) % Cout);
+    const int tap = (int)(i / ((int64_t)Cin * Cout));
+    const float v = w[((int64_t)co * Cin + ci) * kk + tap];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pack_weight_f32_kernel(const float* __restrict__ w, int Cout, int Cin, int kk, float* __restrict__ out) {
+  const int64_t n = (int64_t)kk * Cout * Cin;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const int ci = (int)((i / Cout) % Cin);
+    const int tap = (int)(i / ((int64_t)Cin * Cout));
+    out[i] = w[((int64_t)co * Cin + ci) * kk + tap];
+  }
+}
+
+static inline int grid_for(int64_t n, int block, int max_blocks) {
+  int64_t g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+}  // namespace bbdm
+
+using namespace bbdm;
+
+extern "C" {
+
+int bbdm_bridge_q_sample(const float* x0, const float* y, const float* noise, const int64_t* t,
+                         const float* m_t, const float* variance_t, int num_timesteps,
+                         int objective, float* x_t_out, float* objective_out, int B,
+                         int64_t n_per_sample, void* stream) {
+  BBDM_REQUIRE(x0 && y && noise && t && m_t && variance_t && x_t_out && objective_out, "q_sample: null pointer");
+  BBDM_REQUIRE(B > 0 && B <= 65535 && n_per_sample > 0 && n_per_sample % 4 == 0,
+               "q_sample: need 0 < B <= 65535 and n_per_sample %% 4 == 0 (got %d, %lld)", B, (long long)n_per_sample);
+  (void)num_timesteps;
+  const int64_t n4 = n_per_sample / 4;
+  dim3 grid(grid_for(n4, 256, num_sms() * 8), B);
+  cudaStream_t s = (cudaStream_t)stream;
+#define BBDM_QL(O)                                                                              \
+  q_sample_kernel<O><<<grid, 256, 0, s>>>((const float4*)x0, (const float4*)y, (const float4*)noise, t, \
+                                          m_t, variance_t, (float4*)x_t_out, (float4*)objective_out, n4)
+  if (objective == BBDM_OBJ_GRAD) BBDM_QL(BBDM_OBJ_GRAD);
+  else if (objective == BBDM_OBJ_NOISE) BBDM_QL(BBDM_OBJ_NOISE);
+  else if (objective == BBDM_OBJ_YSUBX) BBDM_QL(BBDM_OBJ_YSUBX);
+  else BBDM_REQUIRE(false, "q_sample: unknown objective %d", objective);
+#undef BBDM_QL
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
+int bbdm_bridge_p_sample(const float* x_t, const float* y, const float* eps, const float* noise,
+                         BbdmPSampleCoef coef, int objective, int clip_denoised, int is_last,
+                         float* x_out, float* x0_out, int64_t n, void* stream) {
+  BBDM_REQUIRE(x_t && y && eps && x_out, "p_sample: null pointer");
+  BBDM_REQUIRE(is_last || noise, "p_sample: noise required unless is_last");
+  BBDM_REQUIRE(n > 0 && n % 4 == 0, "p_sample: n %% 4 != 0");
+  BBDM_REQUIRE(objective >= 0 && objective <= 2, "p_sample: unknown objective %d", objective);
+  const int64_t n4 = n / 4;
+  const int grid = grid_for(n4, 256, num_sms() * 8);
+  cudaStream_t s = (cudaStream_t)stream;
+#define BBDM_PL(O, C, L)                                                                     \
+  p_sample_kernel<O, C, L><<<grid, 256, 0, s>>>((const float4*)x_t, (const float4*)y,       \
+                                                (const float4*)eps, (const float4*)noise, coef, \
+                                                (float4*)x_out, (float4*)x0_out, n4)
+#define BBDM_PL2(O)                                      \
+  if (clip_denoised) { if (is_last) BBDM_PL(O, true, true); else BBDM_PL(O, true, false); } \
+  else { if (is_last) BBDM_PL(O, false, true); else BBDM_PL(O, false, false); }
+  if (objective == BBDM_OBJ_GRAD) { BBDM_PL2(BBDM_OBJ_GRAD) }
+  else if (objective == BBDM_OBJ_NOISE) { BBDM_PL2(BBDM_OBJ_NOISE) }
+  else { BBDM_PL2(BBDM_OBJ_YSUBX) }
+#undef BBDM_PL2
+#undef BBDM_PL
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
+int bbdm_nchw_to_nhwc_cat(const float* x, int c1, const float* ctx, int c2, int B, int H, int W,
+                          float* out, void* stream) {
+  BBDM_REQUIRE(x && out && c1 > 0 && (c2 == 0 || ctx) && B > 0 && B <= 65535, "nchw_to_nhwc_cat: bad args");
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid(grid_for(HW, 256, 4096), B);
+  nchw_to_nhwc_cat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, c1, ctx, ctx ? c2 : 0, HW, out);
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
+int bbdm_nhwc_to_nchw(const float* src, int B, int H, int W, int C, float* out, void* stream) {
+  BBDM_REQUIRE(src && out && B > 0 && B <= 65535 && C > 0, "nhwc_to_nchw: bad args");
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid(grid_for(HW, 256, 4096), B);
+  nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, C, HW, out);
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
+int bbdm_gather_rows(const float* table, int rows, int width, const int64_t* idx, int B, float* out,
+                     void* stream) {
+  BBDM_REQUIRE(table && idx && out && rows > 0 && width > 0 && B > 0, "gather_rows: bad args");
+  gather_rows_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(table, rows, width, idx, out);
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
+int bbdm_linear_f32(const float* x, const float* w, const float* bias, float* out, int B, int K,
+                    int N, int act_in, int act_out, void* stream) {
+  BBDM_REQUIRE(x && w && out && B > 0 && K > 0 && N > 0, "linear_f32: bad args");
+  const int warps_per_block = 8;
+  const int grid = (N + warps_per_block - 1) / warps_per_block;
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    linear_f32_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, out, B, K, N, act_in, act_out, b0);
+    BBDM_LAUNCH_CHECK();
+  }
+  return BBDM_OK;
+}
+
+int bbdm_pack_weight_split(const float* w, int Cout, int Cin, int k, void* w_hi, void* w_lo, void* stream) {
+  BBDM_REQUIRE(w && w_hi && w_lo && Cout > 0 && Cin > 0 && (k == 1 || k == 3), "pack_weight_split: bad args");
+  const int64_t n = (int64_t)k * k * Cout * Cin;
+  pack_weight_split_kernel<<<grid_for(n, 256, num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(
+      w, Cout, Cin, k * k, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo);
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
+int bbdm_pack_weight_f32(const float* w, int Cout, int Cin, int k, float* out, void* stream) {
+  BBDM_REQUIRE(w && out && Cout > 0 && Cin > 0 && (k == 1 || k == 3), "pack_weight_f32: bad args");
+  const int64_t n = (int64_t)k * k * Cout * Cin;
+  pack_weight_f32_kernel<<<grid_for(n, 256, num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, k * k, out);
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,383 @@
+"""UNet executor over the C-ABI kernels.
+
+Walks the reference-shaped module tree (bbdm_b200.unet) and issues one C-ABI call per fused
+step.  Data layout inside the UNet: NHWC fp32 activations in HBM; every tensor-core conv reads
+its A operand as a split-bf16 plane pair produced by the one-pass ``prep`` kernel
+(GroupNorm-affine + FiLM + SiLU + up/down-sampling + concat, fused) and writes fp32 NHWC with
+bias / 1x1-skip / residual fused in its epilogue.  See DESIGN.md section "Kernels".
+
+The executor is written against a *backend* object (``cabi.CudaBackend`` -- the only product
+backend).  tests/ inject an oracle-backed emulation of the same method set to verify this host
+logic (block wiring, concat order, FiLM offsets, skip modes) on CPU; the product never does.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import cabi
+from .unet import (AttentionBlock, Downsample, ResBlock, TimestepEmbedSequential, UNetModel,
+                   Upsample, timestep_embedding)
+
+GN_GROUPS = 32
+GN_EPS = 1e-5
+
+
+class _Pool:
+    """Shape-keyed free lists.  The forward pass is the same acquire/release sequence every
+    call, so after the first call no allocation happens and every intermediate keeps a stable
+    address (required for CUDA-graph replay, avoids allocator traffic)."""
+
+    def __init__(self, backend, device):
+        self.be, self.device, self.free = backend, device, {}
+        self.bytes = 0
+
+    def get(self, shape, dtype=torch.float32):
+        key = (tuple(shape), dtype)
+        lst = self.free.get(key)
+        if lst:
+            return lst.pop()
+        t = self.be.empty(tuple(shape), dtype, self.device)
+        self.bytes += t.numel() * t.element_size()
+        return t
+
+    def put(self, *ts):
+        for t in ts:
+            if t is not None:
+                self.free.setdefault((tuple(t.shape), t.dtype), []).append(t)
+
+
+class UNetEngine:
+    def __init__(self, unet: UNetModel, backend=None, precision: str = "split3"):
+        self.unet = unet
+        self.be = backend if backend is not None else cabi.CudaBackend()
+        assert precision in ("split3", "bf16")
+        self.passes = 3 if precision == "split3" else 1
+        self.precision = precision
+        self._wkey = None
+        self._w = {}
+        self._pools = {}
+        self._table = None
+        self._gn_ws = None
+        self.num_timesteps = 1000
+
+    # ------------------------------------------------------------------------------ weights
+    def _params_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.unet.parameters())
+
+    def _umma_ok(self, cin, cout, w):
+        return cin % 64 == 0 and cout % 64 == 0 and w >= 4
+
+    def refresh_weights(self, force=False):
+        """(Re)derive the packed weight caches if any parameter changed (optimizer step, EMA
+        swap, load_state_dict).  The nn.Parameters themselves stay OIHW fp32."""
+        key = self._params_key()
+        if not force and key == self._wkey:
+            return
+        be, u = self.be, self.unet
+        dev = next(u.parameters()).device
+        w = {}
+
+        def pack(conv, name):
+            wt = conv.weight.detach()
+            if wt.dim() == 3:                       # Conv1d [Cout, Cin, 1]
+                wt = wt.unsqueeze(-1)
+            wt = wt.contiguous()
+            cout, cin, k = wt.shape[0], wt.shape[1], wt.shape[2]
+            ent = {"cout": cout, "cin": cin, "k": k, "bias": conv.bias.detach() if conv.bias is not None else None}
+            if cin % 64 == 0 and cout % 64 == 0 and k in (1, 3):
+                hi = be.empty((k * k, cout, cin), torch.bfloat16, dev)
+                lo = be.empty((k * k, cout, cin), torch.bfloat16, dev)
+                be.pack_weight_split(wt, hi, lo)
+                ent["hi"], ent["lo"] = hi, lo
+            f32 = be.empty((k * k, cin, cout), torch.float32, dev)
+            be.pack_weight_f32(wt, f32)
+            ent["f32"] = f32
+            w[name] = ent
+
+        film_w, film_b, off = [], [], 0
+        for name, m in u.named_modules():
+            if isinstance(m, (nn.Conv2d, nn.Conv1d)):
+                pack(m, name)
+            if isinstance(m, ResBlock):
+                lin = m.emb_layers[1]
+                n = lin.weight.shape[0]
+                assert n % 4 == 0
+                b = lin.bias.detach()
+                if not m.use_scale_shift_norm:
+                    # h + emb_out happens before out_layers' GroupNorm: fold conv1's bias into the
+                    # per-sample vector so conv1 can take it as its (per-sample) bias directly
+                    b = b + m.in_layers[2].bias.detach()
+                film_w.append(lin.weight.detach())
+                film_b.append(b)
+                w[name + "#film"] = (off, n)
+                off += n
+        w["film_w"] = torch.cat(film_w, 0).contiguous()
+        w["film_b"] = torch.cat(film_b, 0).contiguous()
+        w["film_n"] = off
+        self._w = w
+        self._wkey = key
+        if self._table is None or self._table.shape[0] < self.num_timesteps or self._table.device != dev:
+            # host-built with the reference's own expression (util.py:151-171): indexing is exact
+            tab = timestep_embedding(torch.arange(self.num_timesteps), u.model_channels)
+            self._table = tab.to(dev).contiguous()
+
+    # ------------------------------------------------------------------------------ helpers
+    def _pool(self, device):
+        p = self._pools.get(device)
+        if p is None:
+            p = self._pools[device] = _Pool(self.be, device)
+        return p
+
+    def _stats(self, pool, src1, src2):
+        B = src1.shape[0]
+        mean, rstd = pool.get((B, GN_GROUPS)), pool.get((B, GN_GROUPS))
+        if self._gn_ws is None or self._gn_ws.numel() < B * GN_GROUPS * cabi.GN_MAX_SLICES * 2 \
+                or self._gn_ws.device != src1.device:
+            self._gn_ws = self.be.empty((B * GN_GROUPS * cabi.GN_MAX_SLICES * 2,), torch.float64, src1.device)
+        self.be.gn_stats(src1, src2, GN_GROUPS, GN_EPS, mean, rstd, self._gn_ws)
+        return mean, rstd
+
+    def _conv(self, pool, ent, *, a_f32=None, a_hi=None, a_lo=None, shape, bias=None, residual=None,
+              res_mode=cabi.RES_NONE, second=None, out_split=False, want_f32=True, stride=1, out=None):
+        """One convolution.  shape = (B,H,W) of the INPUT; returns (out_f32, out_hi, out_lo)."""
+        B, H, W = shape
+        cout, cin, k = ent["cout"], ent["cin"], ent["k"]
+        bias = ent["bias"] if bias is None else bias
+        if a_hi is not None:
+            if out is None:
+                out = pool.get((B, H, W, cout)) if want_f32 else None
+            oh = ol = None
+            if out_split:
+                oh, ol = pool.get((B, H, W, cout), torch.bfloat16), pool.get((B, H, W, cout), torch.bfloat16)
+            kw = {}
+            if second is not None:
+                e2, r_hi, r_lo = second
+                kw = dict(Cin2=e2["cin"], a2_hi=r_hi, a2_lo=r_lo, w2_hi=e2["hi"], w2_lo=e2["lo"], bias2=e2["bias"])
+            self.be.conv_umma(B=B, H=H, W=W, Cin=cin, Cout=cout, taps=k * k, a_hi=a_hi, a_lo=a_lo,
+                              w_hi=ent["hi"], w_lo=ent["lo"], bias=bias, residual=residual, res_mode=res_mode,
+                              out=out, out_hi=oh, out_lo=ol, passes=self.passes, **kw)
+            return out, oh, ol
+        assert second is None and res_mode in (cabi.RES_NONE, cabi.RES_SAME) and not out_split
+        Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+        if out is None:
+            out = pool.get((B, Ho, Wo, cout))
+        self.be.conv_direct(a_f32, ent["f32"], bias, residual, out, cout, k, stride)
+        return out, None, None
+
+    # ------------------------------------------------------------------------------ blocks
+    def _resblock(self, pool, name, m: ResBlock, src1, src2, film):
+        be, w = self.be, self._w
+        B, Hs, Ws, c1 = src1.shape
+        c2 = 0 if src2 is None else src2.shape[3]
+        cin, cout = c1 + c2, m.out_channels
+        assert cin == m.channels
+        resample = cabi.RESAMPLE_UP2 if m.up else (cabi.RESAMPLE_DOWN2 if m.down else cabi.RESAMPLE_NONE)
+        H, W = (Hs * 2, Ws * 2) if m.up else ((Hs // 2, Ws // 2) if m.down else (Hs, Ws))
+        e1, e2 = w[name + ".in_layers.2"], w[name + ".out_layers.3"]
+        skip_conv = isinstance(m.skip_connection, nn.Conv2d)
+        es = w[name + ".skip_connection"] if skip_conv else None
+        umma1 = self._umma_ok(cin, cout, W)
+        umma2 = self._umma_ok(cout, cout, W)
+        fuse_skip = skip_conv and umma2 and es["k"] == 1 and cin % 64 == 0
+        need_raw_f32 = (skip_conv and not fuse_skip) or \
+                       (not skip_conv and (src2 is not None or (resample != cabi.RESAMPLE_NONE and not umma2)))
+        foff, fn = w[name + "#film"]
+
+        # ---- in_layers: GN -> SiLU -> (up/down) -> conv3x3 -------------------------------------
+        mean, rstd = self._stats(pool, src1, src2)
+        gn = m.in_layers[0]
+        shp = (B, H, W, cin)
+        a_f32 = a_hi = a_lo = r_f32 = r_hi = r_lo = None
+        if umma1:
+            a_hi, a_lo = pool.get(shp, torch.bfloat16), pool.get(shp, torch.bfloat16)
+        else:
+            a_f32 = pool.get(shp)
+        if fuse_skip:
+            r_hi, r_lo = pool.get(shp, torch.bfloat16), pool.get(shp, torch.bfloat16)
+        if need_raw_f32:
+            r_f32 = pool.get(shp)
+        be.prep(src1, src2, groups=GN_GROUPS, mean=mean, rstd=rstd, gamma=gn.weight.detach(), beta=gn.bias.detach(),
+                silu=True, resample=resample, act_f32=a_f32, act_hi=a_hi, act_lo=a_lo,
+                raw_f32=r_f32, raw_hi=r_hi, raw_lo=r_lo)
+        pool.put(mean, rstd)
+        if m.use_scale_shift_norm:
+            h1, _, _ = self._conv(pool, e1, a_f32=a_f32, a_hi=a_hi, a_lo=a_lo, shape=(B, H, W))
+        else:
+            # conv1 + (bias + emb_out[b]) per sample: per-sample bias rows live in `film`
+            h1 = pool.get((B, H, W, cout))
+            for b in range(B):
+                sl = lambda z: None if z is None else z[b:b + 1]
+                self._conv(pool, e1, a_f32=sl(a_f32), a_hi=sl(a_hi), a_lo=sl(a_lo), shape=(1, H, W),
+                           bias=film[b, foff:foff + fn], out=h1[b:b + 1])
+        pool.put(a_f32, a_hi, a_lo)
+
+        # ---- out_layers: GN (+FiLM) -> SiLU -> conv3x3 (+skip) -----------------------------------
+        mean, rstd = self._stats(pool, h1, None)
+        gn2 = m.out_layers[0]
+        shp2 = (B, H, W, cout)
+        b_f32 = b_hi = b_lo = None
+        if umma2:
+            b_hi, b_lo = pool.get(shp2, torch.bfloat16), pool.get(shp2, torch.bfloat16)
+        else:
+            b_f32 = pool.get(shp2)
+        fkw = {}
+        if m.use_scale_shift_norm:
+            fkw = dict(film_scale=film[:, foff:foff + cout], film_shift=film[:, foff + cout:foff + 2 * cout],
+                       film_stride=film.shape[1])
+        be.prep(h1, None, groups=GN_GROUPS, mean=mean, rstd=rstd, gamma=gn2.weight.detach(), beta=gn2.bias.detach(),
+                silu=True, resample=cabi.RESAMPLE_NONE, act_f32=b_f32, act_hi=b_hi, act_lo=b_lo, **fkw)
+        pool.put(mean, rstd, h1)
+
+        residual, res_mode, second, skip_out = None, cabi.RES_NONE, None, None
+        if fuse_skip:
+            second = (es, r_hi, r_lo)
+        elif skip_conv:
+            skip_out, _, _ = self._conv(pool, es, a_f32=r_f32, shape=(B, H, W))
+            residual, res_mode = skip_out, cabi.RES_SAME
+        elif need_raw_f32:
+            residual, res_mode = r_f32, cabi.RES_SAME
+        else:
+            residual = src1
+            res_mode = {cabi.RESAMPLE_NONE: cabi.RES_SAME, cabi.RESAMPLE_UP2: cabi.RES_UP2,
+                        cabi.RESAMPLE_DOWN2: cabi.RES_DOWN2}[resample]
+        out, _, _ = self._conv(pool, e2, a_f32=b_f32, a_hi=b_hi, a_lo=b_lo, shape=(B, H, W),
+                               residual=residual, res_mode=res_mode, second=second)
+        pool.put(b_f32, b_hi, b_lo, r_f32, r_hi, r_lo, skip_out)
+        return out
+
+    def _attention(self, pool, name, m: AttentionBlock, x):
+        be, w = self.be, self._w
+        B, H, W, Cc = x.shape
+        T = H * W
+        eq, ep = w[name + ".qkv"], w[name + ".proj_out"]
+        heads = m.num_heads
+        hd = Cc // heads
+        if hd not in (16, 32, 64):
+            raise NotImplementedError(f"attention head_dim {hd}: the sm_100a kernel supports 16/32/64")
+        umma = self._umma_ok(Cc, Cc, W)
+        mean, rstd = self._stats(pool, x, None)
+        a_f32 = a_hi = a_lo = None
+        if umma:
+            a_hi, a_lo = pool.get(x.shape, torch.bfloat16), pool.get(x.shape, torch.bfloat16)
+        else:
+            a_f32 = pool.get(x.shape)
+        be.prep(x, None, groups=GN_GROUPS, mean=mean, rstd=rstd, gamma=m.norm.weight.detach(),
+                beta=m.norm.bias.detach(), silu=False, resample=cabi.RESAMPLE_NONE,
+                act_f32=a_f32, act_hi=a_hi, act_lo=a_lo)
+        pool.put(mean, rstd)
+        qkv, _, _ = self._conv(pool, eq, a_f32=a_f32, a_hi=a_hi, a_lo=a_lo, shape=(B, H, W))
+        pool.put(a_f32, a_hi, a_lo)
+        o_f32 = o_hi = o_lo = None
+        if umma:
+            o_hi, o_lo = pool.get(x.shape, torch.bfloat16), pool.get(x.shape, torch.bfloat16)
+        else:
+            o_f32 = pool.get(x.shape)
+        be.attention(qkv.view(B, T, 3 * Cc), heads, 1 if m.new_order else 0,
+                     None if o_f32 is None else o_f32.view(B, T, Cc),
+                     None if o_hi is None else o_hi.view(B, T, Cc),
+                     None if o_lo is None else o_lo.view(B, T, Cc))
+        pool.put(qkv)
+        out, _, _ = self._conv(pool, ep, a_f32=o_f32, a_hi=o_hi, a_lo=o_lo, shape=(B, H, W),
+                               residual=x, res_mode=cabi.RES_SAME)
+        pool.put(o_f32, o_hi, o_lo)
+        return out
+
+    def _resample_layer(self, pool, name, m, x):
+        be, w = self.be, self._w
+        B, H, W, Cc = x.shape
+        if isinstance(m, Downsample):
+            if m.use_conv:
+                out, _, _ = self._conv(pool, w[name + ".op"], a_f32=x, shape=(B, H, W), stride=2)
+                return out
+            out = pool.get((B, H // 2, W // 2, Cc))
+            be.prep(x, None, resample=cabi.RESAMPLE_DOWN2, raw_f32=out)
+            return out
+        up = pool.get((B, H * 2, W * 2, Cc))
+        be.prep(x, None, resample=cabi.RESAMPLE_UP2, raw_f32=up)
+        if not m.use_conv:
+            return up
+        out, _, _ = self._conv(pool, w[name + ".conv"], a_f32=up, shape=(B, H * 2, W * 2))
+        pool.put(up)
+        return out
+
+    def _run_block(self, pool, prefix, block: TimestepEmbedSequential, h, skip, film, release_input):
+        """h (+ skip, channel-concatenated behind it for the first layer) through one block.
+        release_input: whether h/skip may go back to the pool once the first layer has consumed
+        them (False while they are still referenced as saved skip tensors)."""
+        cur, cur_skip, owned = h, skip, release_input
+        for j, layer in enumerate(block):
+            name = f"{prefix}.{j}"
+            if isinstance(layer, ResBlock):
+                new = self._resblock(pool, name, layer, cur, cur_skip, film)
+            else:
+                assert cur_skip is None, "a concatenated input is only consumed by a ResBlock"
+                if isinstance(layer, AttentionBlock):
+                    new = self._attention(pool, name, layer, cur)
+                elif isinstance(layer, (Downsample, Upsample)):
+                    new = self._resample_layer(pool, name, layer, cur)
+                elif isinstance(layer, nn.Conv2d):
+                    new, _, _ = self._conv(pool, self._w[name], a_f32=cur, shape=cur.shape[:3])
+                else:
+                    raise NotImplementedError(type(layer).__name__)
+            if owned:
+                pool.put(cur, cur_skip)
+            cur, cur_skip, owned = new, None, True
+        return cur
+
+    # ------------------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, x, timesteps, context=None, assume_fresh_weights=False, out=None):
+        u, be = self.unet, self.be
+        if not assume_fresh_weights:
+            self.refresh_weights()
+        w = self._w
+        dev = x.device
+        pool = self._pool(dev)
+        x = x.contiguous().float()
+        B, Cx, H, W = x.shape
+        ctx = None
+        if u.condition_key != "nocond":
+            ctx = context.contiguous().float()
+        t = timesteps.to(device=dev, dtype=torch.int64).contiguous()
+
+        # ---- timestep embedding MLP + all FiLM projections (3 small fp32 GEMV launches) --------
+        mc, ted = u.model_channels, u.model_channels * 4
+        temb, e1, emb = pool.get((B, mc)), pool.get((B, ted)), pool.get((B, ted))
+        film = pool.get((B, w["film_n"]))
+        be.gather_rows(self._table, t, temb)
+        l0, l2 = u.time_embed[0], u.time_embed[2]
+        be.linear(temb, l0.weight.detach(), l0.bias.detach(), e1, act_out=True)
+        be.linear(e1, l2.weight.detach(), l2.bias.detach(), emb)
+        be.linear(emb, w["film_w"], w["film_b"], film, act_in=True)
+        pool.put(temb, e1)
+
+        # ---- stem --------------------------------------------------------------------------------
+        cin0 = Cx + (0 if ctx is None else ctx.shape[1])
+        xin = pool.get((B, H, W, cin0))
+        be.nchw_to_nhwc_cat(x, ctx, xin)
+        hs = []
+        h = xin
+        for i, block in enumerate(u.input_blocks):
+            # block inputs after the stem are saved skip tensors (hs): not released here
+            h = self._run_block(pool, f"input_blocks.{i}", block, h, None, film, release_input=(i == 0))
+            hs.append(h)
+        h = self._run_block(pool, "middle_block", u.middle_block, h, None, film, release_input=False)
+        for i, block in enumerate(u.output_blocks):
+            # h is the previous block's output, hs.pop() the matching skip: both die here
+            h = self._run_block(pool, f"output_blocks.{i}", block, h, hs.pop(), film, release_input=True)
+
+        # ---- head: GN -> SiLU -> conv3x3 -> NCHW ----------------------------------------------------
+        mean, rstd = self._stats(pool, h, None)
+        gn = u.out[0]
+        act = pool.get(h.shape)
+        be.prep(h, None, groups=GN_GROUPS, mean=mean, rstd=rstd, gamma=gn.weight.detach(), beta=gn.bias.detach(),
+                silu=True, resample=cabi.RESAMPLE_NONE, act_f32=act)
+        pool.put(mean, rstd, h)
+        y, _, _ = self._conv(pool, w["out.2"], a_f32=act, shape=(B, H, W))
+        pool.put(act)
+        if out is None:
+            out = torch.empty((B, u.out_channels, H, W), dtype=torch.float32, device=dev)
+        be.nhwc_to_nchw(y, out)
+        pool.put(y, emb, film)
+        return out

@@ -1,0 +1,209 @@
+/*
+ * bbdm_b200.h -- C ABI of the B200-native (sm_100a) BBDM hot path.
+ *
+ * The reference (xuekt98/BBDM) is pure Python/PyTorch: it has no FFI layer.  Its "plugin
+ * boundary" for this path is the Python class contract consumed by the runner (SURVEY.md
+ * section 8b).  This header is the boundary *below* that contract: every device computation the
+ * drop-in classes perform goes through exactly these entry points (bound with ctypes in
+ * bbdm_b200/cabi.py).  Each entry point cites the reference code it replaces
+ * (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - plain pointers + sizes only; all pointers are DEVICE pointers unless noted
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous and
+ *     stream-ordered, allocates nothing, and is CUDA-graph capturable
+ *   - return 0 on success, a negative BBDM_E_* code otherwise; bbdm_last_error() returns a
+ *     thread-local message; no exceptions cross the boundary
+ *   - activations inside the UNet are NHWC fp32 ("[B,H,W,C]"); tensor-core operands are the
+ *     same tensors split into two bf16 planes  hi = bf16(x), lo = bf16(x - hi)
+ */
+#ifndef BBDM_B200_H_
+#define BBDM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BBDM_ABI_VERSION 1
+
+enum {
+  BBDM_OK = 0,
+  BBDM_E_INVALID = -1,     /* bad argument / unsupported shape            */
+  BBDM_E_CUDA = -2,        /* a CUDA runtime/driver call failed           */
+  BBDM_E_UNSUPPORTED = -3, /* valid request this build cannot serve       */
+  BBDM_E_DEVICE = -4       /* a kernel reported an internal fault/timeout */
+};
+
+int bbdm_abi_version(void);
+const char* bbdm_last_error(void);
+/* Fills sm count / compute capability of the current device; 0 on success. */
+int bbdm_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Reads (and clears) the device-side fault word written by kernels whose mbarrier waits
+ * timed out; synchronises `stream`.  0 = no fault. */
+int bbdm_check_device_fault(void* stream, unsigned long long* fault_word);
+
+/* ------------------------------------------------------------------------------------------
+ * Brownian-bridge elementwise kernels (NCHW fp32, any contiguous [B, n_per_sample])
+ * ------------------------------------------------------------------------------------------ */
+
+enum { BBDM_OBJ_GRAD = 0, BBDM_OBJ_NOISE = 1, BBDM_OBJ_YSUBX = 2 };
+
+/* q_sample: x_t = (1-m_t) x0 + m_t y + sqrt(var_t) noise, plus the training objective.
+ * Replaces BrownianBridgeModel.q_sample (model/BrownianBridge/BrownianBridgeModel.py:128-146)
+ * and extract() (model/utils.py:4-7).  t: int64 [B]; m_t/variance_t: fp32 [T] schedule buffers.
+ * Same fp32 operation order as the reference => bit-exact. */
+int bbdm_bridge_q_sample(const float* x0, const float* y, const float* noise, const int64_t* t,
+                         const float* m_t, const float* variance_t, int num_timesteps,
+                         int objective, float* x_t_out, float* objective_out,
+                         int B, int64_t n_per_sample, void* stream);
+
+/* Per-step scalar coefficients of the reverse bridge update (host computes them in fp32 with
+ * the reference's expression order; BrownianBridgeModel.py:190-199). */
+typedef struct {
+  float m_t, one_minus_m_t, sqrt_var_t; /* for predict_x0 (objective 'noise')      */
+  float m_nt, one_minus_m_nt;           /* next-step bridge weights                */
+  float c_xt;                           /* sqrt((var_nt - sigma2_t) / var_t)       */
+  float sigma_t;                        /* sqrt(sigma2_t) * eta                    */
+} BbdmPSampleCoef;
+
+/* p_sample update: x0_recon = predict_x0(x_t, y, eps) [clamp], then either return x0_recon
+ * (is_last) or the posterior mean + sigma_t * noise.
+ * Replaces predict_x0_from_objective + the tail of p_sample
+ * (BrownianBridgeModel.py:148-160, 171-201).  x0_out may be NULL. noise may be NULL iff is_last. */
+int bbdm_bridge_p_sample(const float* x_t, const float* y, const float* eps, const float* noise,
+                         BbdmPSampleCoef coef, int objective, int clip_denoised, int is_last,
+                         float* x_out, float* x0_out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout / small dense ops
+ * ------------------------------------------------------------------------------------------ */
+
+/* NCHW x [B,c1,H,W] (+ NCHW ctx [B,c2,H,W], may be NULL) -> NHWC [B,H,W,c1+c2].
+ * Replaces th.cat([x, context], dim=1) at openaimodel.py:741-742 + the layout change. */
+int bbdm_nchw_to_nhwc_cat(const float* x, int c1, const float* ctx, int c2, int B, int H, int W,
+                          float* out, void* stream);
+int bbdm_nhwc_to_nchw(const float* src, int B, int H, int W, int C, float* out, void* stream);
+
+/* out[b,:] = table[idx[b],:]  (timestep-embedding table lookup; table built on the host with
+ * the reference's own expression, util.py:151-171, so indexing is bit-exact). */
+int bbdm_gather_rows(const float* table, int rows, int width, const int64_t* idx, int B,
+                     float* out, void* stream);
+
+/* out[B,N] = act_in(x)[B,K] @ w[N,K]^T + bias[N]; act_in: 0 none, 1 SiLU; act_out likewise.
+ * fp32 FMA on CUDA cores.  Replaces time_embed (openaimodel.py:511-516) and every
+ * ResBlock.emb_layers (openaimodel.py:221-227; all 21 concatenated into one call). */
+int bbdm_linear_f32(const float* x, const float* w, const float* bias, float* out,
+                    int B, int K, int N, int act_in, int act_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GroupNorm statistics and the fused "operand preparation" pass
+ * ------------------------------------------------------------------------------------------ */
+
+/* mean/rstd [B,groups] over the channel-concatenation of src1 [B,H,W,c1] and src2 [B,H,W,c2]
+ * (src2 may be NULL), biased variance, rstd = 1/sqrt(var+eps).
+ * Replaces the statistics half of GroupNorm32 (util.py:199-216; nn.GroupNorm(32,C), eps 1e-5).
+ * fp64 accumulation, fixed reduction order (run-to-run deterministic).
+ * workspace: >= B*groups*BBDM_GN_MAX_SLICES*2 doubles. */
+#define BBDM_GN_MAX_SLICES 64
+int bbdm_gn_stats(const float* src1, int c1, const float* src2, int c2, int B, int H, int W,
+                  int groups, float eps, float* mean, float* rstd, double* workspace,
+                  void* stream);
+
+enum { BBDM_RESAMPLE_NONE = 0, BBDM_RESAMPLE_UP2 = 1, BBDM_RESAMPLE_DOWN2 = 2 };
+
+/* One pass over cat(src1, src2) [B,Hs,Ws,C] producing up to two results at the resampled
+ * size [B,H,W,C]:
+ *   act = resample( silu?( GN_affine(x) * (1+film_scale) + film_shift ) )
+ *   raw = resample( x )
+ * each as fp32 and/or as a split-bf16 pair.  mean == NULL skips the "act" result.
+ * Replaces: GroupNorm affine + SiLU (openaimodel.py:205-206,229-230,688-689), the FiLM
+ * scale-shift (:270-274), h_upd/x_upd = Upsample/Downsample without conv (:212-217, 93-163)
+ * and th.cat([h, hs.pop()], 1) (:752). */
+typedef struct {
+  const float* src1; int c1;
+  const float* src2; int c2;
+  int B, Hs, Ws;
+  int groups;
+  const float* mean;         /* [B,groups] or NULL */
+  const float* rstd;
+  const float* gamma;        /* [C] */
+  const float* beta;         /* [C] */
+  const float* film_scale;   /* row b at film_scale + b*film_stride, [C]; NULL = no FiLM */
+  const float* film_shift;
+  int64_t film_stride;
+  int silu;
+  int resample;
+  float* act_f32; void* act_hi; void* act_lo;   /* any may be NULL */
+  float* raw_f32; void* raw_hi; void* raw_lo;
+} BbdmPrepArgs;
+int bbdm_prep_operand(const BbdmPrepArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolutions
+ * ------------------------------------------------------------------------------------------ */
+
+/* Weight repacking (derived caches; the nn.Parameter stays OIHW fp32 so checkpoints/EMA are
+ * unchanged).  w: [Cout,Cin,k,k] fp32 (k = 1 or 3).
+ *   split:  hi/lo bf16 [k*k][Cout][Cin]   (K-major B operand of the tensor-core kernel)
+ *   f32:    fp32 [k*k][Cin][Cout]         (direct kernel) */
+int bbdm_pack_weight_split(const float* w, int Cout, int Cin, int k, void* w_hi, void* w_lo,
+                           void* stream);
+int bbdm_pack_weight_f32(const float* w, int Cout, int Cin, int k, float* out, void* stream);
+
+enum { BBDM_RES_NONE = 0, BBDM_RES_SAME = 1, BBDM_RES_UP2 = 2, BBDM_RES_DOWN2 = 3 };
+
+/* Stride-1 "same" convolution as an implicit GEMM on tcgen05 tensor cores:
+ *   out[b,h,w,:] = sum_taps A[b,h+dy,w+dx,:] . W[tap] + bias
+ *                  (+ A2[b,h,w,:] . W2 + bias2)            fused 1x1 skip conv
+ *                  (+ residual, optionally nearest-up / 2x2-avg resampled)
+ * M = B*H*W (tile 128 = box of pixels), N = Cout, K = taps*Cin (+ Cin2); operands arrive by
+ * TMA (4-D tiled maps, OOB zero fill = the conv padding), accumulate in TMEM (fp32).
+ * passes = 3: A_hi.W_hi + A_lo.W_hi + A_hi.W_lo  (fp32-class accuracy, the parity mode)
+ * passes = 1: A_hi.W_hi                           (plain bf16)
+ * Requirements: Cin % 64 == 0, Cin2 % 64 == 0, Cout % 16 == 0, taps in {1, 9}.
+ * Replaces nn.Conv2d 3x3 / 1x1 in ResBlock (openaimodel.py:207,233,244), the qkv / proj_out
+ * nn.Conv1d of AttentionBlock (:307,315) and the residual adds (:278,327). */
+typedef struct {
+  int B, H, W;
+  int Cin, Cout, taps;
+  const void* a_hi; const void* a_lo;
+  const void* w_hi; const void* w_lo;
+  const float* bias;
+  int Cin2;
+  const void* a2_hi; const void* a2_lo;
+  const void* w2_hi; const void* w2_lo;
+  const float* bias2;
+  const float* residual; int res_mode;
+  float* out;                 /* fp32 [B,H,W,Cout] or NULL                   */
+  void* out_hi; void* out_lo; /* optional split-bf16 copy of the result      */
+  int passes;
+} BbdmConvArgs;
+int bbdm_conv_umma(const BbdmConvArgs* a, void* stream);
+
+/* General fp32 direct convolution on CUDA cores (any Cin/Cout, k in {1,3}, stride 1 or 2,
+ * pad k/2): stem (openaimodel.py:524), head (:690), conv-mode Downsample/Upsample (:109,150)
+ * and channel counts the tensor-core kernel does not take.  src NHWC fp32 [B,H,W,Cin],
+ * w_packed from bbdm_pack_weight_f32, out [B,Ho,Wo,Cout]; residual [B,Ho,Wo,Cout] or NULL. */
+int bbdm_conv_direct(const float* src, const float* w_packed, const float* bias,
+                     const float* residual, float* out, int B, int H, int W, int Cin, int Cout,
+                     int k, int stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Attention core
+ * ------------------------------------------------------------------------------------------ */
+
+/* softmax((q*s)(k*s)^T) v per head, s = head_dim^-1/4, fp32 softmax, flash-style (no T x T
+ * buffer).  qkv: fp32 [B,T,3C] in the channel order of the reference's qkv conv:
+ *   order 0 (QKVAttentionLegacy, openaimodel.py:350-375): [head][q|k|v][head_dim]
+ *   order 1 (QKVAttention, :382-413):                      [q|k|v][head][head_dim]
+ * out: fp32 [B,T,C] and/or split bf16 (A operand of the proj_out GEMM).
+ * Split-bf16 tensor-core products with fp32 accumulation.  head_dim in {16,32,64}. */
+int bbdm_attention(const float* qkv, int B, int T, int C, int heads, int order,
+                   float* out_f32, void* out_hi, void* out_lo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBDM_B200_H_ */

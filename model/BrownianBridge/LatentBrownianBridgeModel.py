@@ -1,0 +1,136 @@
+"""Drop-in ``LatentBrownianBridgeModel``: the latent-space wrapper around the B200-native
+bridge model.  Same surface as the reference class
+(/root/reference/model/BrownianBridge/LatentBrownianBridgeModel.py:19-132): frozen VQGAN
+encode/decode at both ends (kept as the reference's own PyTorch ``VQModel`` per the north star),
+optional cond-stage model, ``encode`` / ``decode`` / ``sample`` / ``sample_vqgan`` /
+``get_ema_net`` and the latent mean/std attributes the runner assigns
+(BBDMRunner.py:41-44,136-158).  Everything between encode and decode -- q_sample, the UNet,
+the p_sample loop -- runs on the sm_100a kernels via the base class.
+"""
+import itertools
+
+import torch
+
+from bbdm_b200.cond import SpatialRescaler
+from model.BrownianBridge.BrownianBridgeModel import BrownianBridgeModel
+
+try:
+    from tqdm.autonotebook import tqdm
+except Exception:  # pragma: no cover
+    def tqdm(it, **kw):
+        return it
+
+
+def _frozen_train(self, mode=True):
+    """train()/eval() become no-ops on the frozen autoencoder."""
+    return self
+
+
+def _load_vqmodel():
+    try:
+        from model.VQGAN.vqgan import VQModel   # the reference's module, unmodified
+    except ImportError as e:  # pragma: no cover - depends on deployment
+        raise ImportError(
+            "LatentBrownianBridgeModel needs the reference's frozen VQGAN (model.VQGAN.vqgan.VQModel): "
+            "put the BBDM checkout on sys.path behind this repo (see INTEGRATION.md)") from e
+    return VQModel
+
+
+class LatentBrownianBridgeModel(BrownianBridgeModel):
+    def __init__(self, model_config):
+        super().__init__(model_config)
+        self.vqgan = _load_vqmodel()(**vars(model_config.VQGAN.params)).eval()
+        self.vqgan.train = _frozen_train
+        for param in self.vqgan.parameters():
+            param.requires_grad = False
+        print(f"load vqgan from {model_config.VQGAN.params.ckpt_path}")
+
+        if self.condition_key == 'nocond':
+            self.cond_stage_model = None
+        elif self.condition_key == 'first_stage':
+            self.cond_stage_model = self.vqgan
+        elif self.condition_key == 'SpatialRescaler':
+            self.cond_stage_model = SpatialRescaler(**vars(model_config.CondStageParams))
+        else:
+            raise NotImplementedError
+
+    def get_ema_net(self):
+        return self
+
+    def get_parameters(self):
+        if self.condition_key == 'SpatialRescaler':
+            print("get parameters to optimize: SpatialRescaler, UNet")
+            return itertools.chain(self.denoise_fn.parameters(), self.cond_stage_model.parameters())
+        print("get parameters to optimize: UNet")
+        return self.denoise_fn.parameters()
+
+    def apply(self, weights_init):
+        super().apply(weights_init)
+        if self.cond_stage_model is not None:
+            # NB: with condition_key 'first_stage' this re-initialises the VQGAN, exactly
+            # as the reference does (:51-55).
+            self.cond_stage_model.apply(weights_init)
+        return self
+
+    # ---- training: both encodes are no-grad, only the UNet (+ rescaler) trains -----------------------
+    def forward(self, x, x_cond, context=None):
+        with torch.no_grad():
+            x_latent = self.encode(x, cond=False)
+            x_cond_latent = self.encode(x_cond, cond=True)
+        context = self.get_cond_stage_context(x_cond)
+        return super().forward(x_latent.detach(), x_cond_latent.detach(), context)
+
+    def get_cond_stage_context(self, x_cond):
+        if self.cond_stage_model is None:
+            return None
+        context = self.cond_stage_model(x_cond)
+        return context.detach() if self.condition_key == 'first_stage' else context
+
+    # ---- frozen autoencoder ends ------------------------------------------------------------------------
+    def _norm_stats(self, cond):
+        if cond:
+            return self.cond_latent_mean, self.cond_latent_std
+        return self.ori_latent_mean, self.ori_latent_std
+
+    @torch.no_grad()
+    def encode(self, x, cond=True, normalize=None):
+        normalize = self.model_config.normalize_latent if normalize is None else normalize
+        z = self.vqgan.encoder(x)
+        if not self.model_config.latent_before_quant_conv:
+            z = self.vqgan.quant_conv(z)
+        if normalize:
+            mean, std = self._norm_stats(cond)
+            z = (z - mean) / std
+        return z
+
+    @torch.no_grad()
+    def decode(self, x_latent, cond=True, normalize=None):
+        normalize = self.model_config.normalize_latent if normalize is None else normalize
+        if normalize:
+            mean, std = self._norm_stats(cond)
+            x_latent = x_latent * std + mean
+        if self.model_config.latent_before_quant_conv:
+            x_latent = self.vqgan.quant_conv(x_latent)
+        x_latent_quant, _, _ = self.vqgan.quantize(x_latent)
+        return self.vqgan.decode(x_latent_quant)
+
+    @torch.no_grad()
+    def sample(self, x_cond, clip_denoised=False, sample_mid_step=False):
+        """NB: no ``context`` argument and clip_denoised defaults to False here (reference :102)."""
+        x_cond_latent = self.encode(x_cond, cond=True)
+        result = self.p_sample_loop(y=x_cond_latent, context=self.get_cond_stage_context(x_cond),
+                                    clip_denoised=clip_denoised, sample_mid_step=sample_mid_step)
+        if not sample_mid_step:
+            return self.decode(result, cond=False)
+        decoded = []
+        for seq, desc in zip(result, ("save output sample mid steps", "save one step sample mid steps")):
+            outs = []
+            for z in tqdm(seq, initial=0, desc=desc, dynamic_ncols=True, smoothing=0.01):
+                outs.append(self.decode(z.detach(), cond=False).to('cpu'))
+            decoded.append(outs)
+        return decoded[0], decoded[1]
+
+    @torch.no_grad()
+    def sample_vqgan(self, x):
+        x_rec, _ = self.vqgan(x)
+        return x_rec

@@ -1,0 +1,169 @@
+"""TEST-ONLY emulation of cabi.CudaBackend on CPU tensors, built on the oracle's per-kernel
+restatements.  It lets the not-gpu suite verify the engine's host logic (block wiring, FiLM
+offsets, concat order, skip/residual modes, buffer lifetimes) without a GPU.  It lives under
+tests/ and is never imported by the product."""
+import torch
+import torch.nn.functional as F
+
+from oracle import bbdm_oracle as O
+
+RESAMPLE = {0: 0, 1: 1, 2: 2}
+
+
+class EmuBackend:
+    name = "oracle-emulation (tests only)"
+
+    def __init__(self, split_emulation=False):
+        self.calls = []
+        self.split = split_emulation   # True: emulate the split-bf16 rounding of the operands
+
+    def empty(self, shape, dtype, device):
+        # poison so that reading an unwritten / prematurely recycled buffer shows up as NaN
+        t = torch.empty(shape, dtype=dtype, device="cpu")
+        if dtype.is_floating_point:
+            t.fill_(float("nan"))
+        return t
+
+    def _planes(self, hi, lo):
+        return hi.float() + lo.float()
+
+    def _write_split(self, x, hi, lo):
+        h, l = O.bf16_split(x.float())
+        hi.copy_(h.to(torch.bfloat16))
+        lo.copy_(l.to(torch.bfloat16))
+
+    # -- bridge ----------------------------------------------------------------------------------
+    def q_sample(self, x0, y, noise, t, m_t, var_t, objective, xt_out, obj_out):
+        self.calls.append("q_sample")
+        xt, obj = O.q_sample({"m_t": m_t, "variance_t": var_t}, x0, y, t, noise, objective)
+        xt_out.copy_(xt)
+        obj_out.copy_(obj)
+
+    def p_sample(self, x_t, y, eps, noise, coef, objective, clip, is_last, x_out, x0_out):
+        self.calls.append("p_sample")
+        m_t, om_t, sq, m_nt, om_nt, c_xt, sigma = [torch.tensor(float(v), dtype=torch.float32) for v in coef]
+        if objective == "grad":
+            x0 = x_t - eps
+        elif objective == "noise":
+            x0 = (x_t - m_t * y - sq * eps) / om_t
+        else:
+            x0 = y - eps
+        if clip:
+            x0 = x0.clamp(-1.0, 1.0)
+        if x0_out is not None:
+            x0_out.copy_(x0)
+        if is_last:
+            x_out.copy_(x0)
+        else:
+            mean = om_nt * x0 + m_nt * y + c_xt * (x_t - om_t * x0 - m_t * y)
+            x_out.copy_(mean + sigma * noise)
+
+    # -- layout / dense ----------------------------------------------------------------------------
+    def nchw_to_nhwc_cat(self, x, ctx, out):
+        self.calls.append("nchw_to_nhwc_cat")
+        z = x if ctx is None else torch.cat([x, ctx], dim=1)
+        out.copy_(z.permute(0, 2, 3, 1))
+
+    def nhwc_to_nchw(self, src, out):
+        self.calls.append("nhwc_to_nchw")
+        assert not torch.isnan(src).any()
+        out.copy_(src.permute(0, 3, 1, 2))
+
+    def gather_rows(self, table, idx, out):
+        self.calls.append("gather_rows")
+        out.copy_(table[idx])
+
+    def linear(self, x, w, bias, out, act_in=False, act_out=False):
+        self.calls.append("linear")
+        z = F.silu(x) if act_in else x
+        z = F.linear(z, w, bias)
+        out.copy_(F.silu(z) if act_out else z)
+
+    # -- group norm / prep ---------------------------------------------------------------------------
+    def gn_stats(self, src1, src2, groups, eps, mean, rstd, workspace):
+        self.calls.append("gn_stats")
+        x = src1 if src2 is None else torch.cat([src1, src2], dim=3)
+        assert not torch.isnan(x).any()
+        m, r = O.op_gn_stats(x, groups, eps)
+        mean.copy_(m)
+        rstd.copy_(r)
+
+    def prep(self, src1, src2, *, groups=32, mean=None, rstd=None, gamma=None, beta=None,
+             film_scale=None, film_shift=None, film_stride=0, silu=True, resample=0,
+             act_f32=None, act_hi=None, act_lo=None, raw_f32=None, raw_hi=None, raw_lo=None):
+        self.calls.append("prep")
+        x = src1 if src2 is None else torch.cat([src1, src2], dim=3)
+        assert not torch.isnan(x).any()
+        if mean is not None:
+            a = O.op_gn_act(x, mean, rstd, gamma, beta, film_scale, film_shift, silu, resample)
+            if act_f32 is not None:
+                act_f32.copy_(a)
+            if act_hi is not None:
+                self._write_split(a, act_hi, act_lo)
+        if raw_f32 is not None or raw_hi is not None:
+            r = O.op_resample(x, resample)
+            if raw_f32 is not None:
+                raw_f32.copy_(r)
+            if raw_hi is not None:
+                self._write_split(r, raw_hi, raw_lo)
+
+    # -- convolutions ----------------------------------------------------------------------------------
+    def pack_weight_split(self, w, hi, lo):
+        self.calls.append("pack_weight_split")
+        cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+        self._write_split(w.permute(2, 3, 0, 1).reshape(k * k, cout, cin), hi, lo)
+
+    def pack_weight_f32(self, w, out):
+        self.calls.append("pack_weight_f32")
+        cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+        out.copy_(w.permute(2, 3, 1, 0).reshape(k * k, cin, cout))
+
+    @staticmethod
+    def _oihw_from_split(hi, lo, taps):
+        k = 3 if taps == 9 else 1
+        w = hi.float() + lo.float()                      # [taps, Cout, Cin]
+        return w.reshape(k, k, w.shape[1], w.shape[2]).permute(2, 3, 0, 1).contiguous()
+
+    def conv_umma(self, *, B, H, W, Cin, Cout, taps, a_hi, a_lo, w_hi, w_lo, bias=None, Cin2=0,
+                  a2_hi=None, a2_lo=None, w2_hi=None, w2_lo=None, bias2=None, residual=None,
+                  res_mode=0, out=None, out_hi=None, out_lo=None, passes=3):
+        self.calls.append("conv_umma")
+        assert Cin % 64 == 0 and Cout % 64 == 0 and Cin2 % 64 == 0 and W >= 4
+        a = self._planes(a_hi, a_lo).reshape(B, H, W, Cin)
+        assert not torch.isnan(a).any()
+        o = O.op_conv_nhwc(a, self._oihw_from_split(w_hi, w_lo, taps), bias)
+        if Cin2:
+            a2 = self._planes(a2_hi, a2_lo).reshape(B, H, W, Cin2)
+            o = o + O.op_conv_nhwc(a2, self._oihw_from_split(w2_hi, w2_lo, 1), bias2)
+        if res_mode == 1:
+            o = o + residual.reshape(B, H, W, Cout)
+        elif res_mode == 2:
+            o = o + O.op_resample(residual.reshape(B, H // 2, W // 2, Cout), 1)
+        elif res_mode == 3:
+            o = o + O.op_resample(residual.reshape(B, H * 2, W * 2, Cout), 2)
+        if out is not None:
+            out.copy_(o.reshape(out.shape))
+        if out_hi is not None:
+            self._write_split(o.reshape(out_hi.shape), out_hi, out_lo)
+
+    def conv_direct(self, src, w_packed, bias, residual, out, Cout, k, stride=1):
+        self.calls.append("conv_direct")
+        assert not torch.isnan(src).any()
+        cin = src.shape[3]
+        w = w_packed.reshape(k, k, cin, Cout).permute(3, 2, 0, 1)
+        o = F.conv2d(src.permute(0, 3, 1, 2), w, bias, stride=stride, padding=k // 2).permute(0, 2, 3, 1)
+        if residual is not None:
+            o = o + residual
+        out.copy_(o)
+
+    # -- attention ----------------------------------------------------------------------------------------
+    def attention(self, qkv, heads, order, out_f32=None, out_hi=None, out_lo=None):
+        self.calls.append("attention")
+        o = O.op_attention_nhwc(qkv, heads, bool(order))
+        if out_f32 is not None:
+            out_f32.copy_(o)
+        if out_hi is not None:
+            self._write_split(o, out_hi, out_lo)
+
+    def check_fault(self):
+        pass

@@ -1,0 +1,265 @@
+"""-m gpu: every C-ABI kernel against its oracle restatement on the same seeded inputs."""
+import math
+import os
+
+import pytest
+import torch
+
+from _recipe import rel_dev
+from oracle import bbdm_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def be():
+    from bbdm_b200 import cabi
+    b = cabi.CudaBackend()
+    yield b
+    b.check_fault()
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (scale * torch.randn(shape, generator=g)).float()
+
+
+# ------------------------------------------------------------------------------------ bridge
+@pytest.mark.parametrize("objective", ["grad", "noise", "ysubx"])
+def test_q_sample_bit_exact(be, objective):
+    bufs, _ = O.make_schedule()
+    B, shape = 5, (5, 3, 24, 24)
+    x0, y, nz = rnd(shape, 1, 0.5), rnd(shape, 2, 0.5), rnd(shape, 3)
+    t = torch.tensor([0, 1, 499, 998, 999])
+    want_xt, want_obj = O.q_sample(bufs, x0, y, t, nz, objective)
+    xt, obj = torch.empty(shape, device=DEV), torch.empty(shape, device=DEV)
+    be.q_sample(x0.to(DEV), y.to(DEV), nz.to(DEV), t.to(DEV), bufs["m_t"].to(DEV), bufs["variance_t"].to(DEV),
+                objective, xt, obj)
+    assert torch.equal(xt.cpu(), want_xt) and torch.equal(obj.cpu(), want_obj)
+
+
+@pytest.mark.parametrize("objective,eta", [("grad", 1.0), ("noise", 1.0), ("ysubx", 0.5)])
+@pytest.mark.parametrize("clip", [False, True])
+def test_p_sample_update_bit_exact(be, objective, eta, clip):
+    from bbdm_b200.schedule import step_coefficients
+    bufs, steps = O.make_schedule(sample_step=50)
+    coef = step_coefficients(bufs["m_t"], bufs["variance_t"], steps, eta)
+    shape = (3, 3, 20, 20)
+    xt, y, eps, nz = rnd(shape, 4, 0.7), rnd(shape, 5, 0.5), rnd(shape, 6, 0.6), rnd(shape, 7)
+    for i in (0, 1, 25, len(steps) - 2, len(steps) - 1):
+        want, want_x0 = O.p_sample_update(bufs, steps, i, xt, y, eps, nz, objective, eta, clip)
+        out, x0 = torch.empty(shape, device=DEV), torch.empty(shape, device=DEV)
+        last = int(steps[i]) == 0
+        be.p_sample(xt.to(DEV), y.to(DEV), eps.to(DEV), None if last else nz.to(DEV), coef[i].tolist(),
+                    objective, clip, last, out, x0)
+        assert torch.equal(x0.cpu(), want_x0), (objective, i)
+        assert torch.equal(out.cpu(), want), (objective, i)
+
+
+# ------------------------------------------------------------------------------------ layout / dense
+def test_layout_roundtrip_and_cat(be):
+    x, c = rnd((3, 3, 10, 12), 8), rnd((3, 5, 10, 12), 9)
+    out = torch.empty((3, 10, 12, 8), device=DEV)
+    be.nchw_to_nhwc_cat(x.to(DEV), c.to(DEV), out)
+    assert torch.equal(out.cpu(), torch.cat([x, c], 1).permute(0, 2, 3, 1).contiguous())
+    back = torch.empty((3, 8, 10, 12), device=DEV)
+    be.nhwc_to_nchw(out, back)
+    assert torch.equal(back.cpu(), torch.cat([x, c], 1))
+    out1 = torch.empty((3, 10, 12, 3), device=DEV)
+    be.nchw_to_nhwc_cat(x.to(DEV), None, out1)
+    assert torch.equal(out1.cpu(), x.permute(0, 2, 3, 1).contiguous())
+
+
+def test_gather_and_linear(be):
+    tab = rnd((1000, 128), 10)
+    idx = torch.tensor([999, 0, 17, 500, 3, 3, 998, 1, 2])
+    out = torch.empty((9, 128), device=DEV)
+    be.gather_rows(tab.to(DEV), idx.to(DEV), out)
+    assert torch.equal(out.cpu(), tab[idx])
+    x, w, b = rnd((9, 128), 11), rnd((515, 128), 12, 0.05), rnd((515,), 13, 0.02)
+    for ai, ao in ((False, False), (True, False), (False, True)):
+        o = torch.empty((9, 515), device=DEV)
+        be.linear(x.to(DEV), w.to(DEV), b.to(DEV), o, act_in=ai, act_out=ao)
+        z = torch.nn.functional.silu(x.double()) if ai else x.double()
+        z = z @ w.double().T + b.double()
+        z = torch.nn.functional.silu(z) if ao else z
+        assert rel_dev(o, z) < 2e-6
+
+
+# ------------------------------------------------------------------------------------ group norm / prep
+@pytest.mark.parametrize("B,H,W,c1,c2", [(2, 16, 16, 128, 0), (3, 8, 8, 512, 128), (2, 4, 4, 32, 0),
+                                         (2, 12, 10, 96, 32), (1, 64, 64, 1024, 512), (2, 8, 8, 35 * 32 // 32 * 32, 0)])
+def test_gn_stats(be, B, H, W, c1, c2):
+    from bbdm_b200 import cabi
+    s1 = rnd((B, H, W, c1), 20) + 0.3
+    s2 = (rnd((B, H, W, c2), 21, 2.0) - 0.5) if c2 else None
+    x = s1 if s2 is None else torch.cat([s1, s2], 3)
+    m_want, r_want = O.op_gn_stats(x)
+    mean, rstd = torch.empty((B, 32), device=DEV), torch.empty((B, 32), device=DEV)
+    ws = torch.empty(B * 32 * cabi.GN_MAX_SLICES * 2, dtype=torch.float64, device=DEV)
+    be.gn_stats(s1.to(DEV), None if s2 is None else s2.to(DEV), 32, 1e-5, mean, rstd, ws)
+    assert (mean.cpu() - m_want).abs().max() < 2e-6 and rel_dev(rstd, r_want) < 2e-6
+    m2, r2 = torch.empty_like(mean), torch.empty_like(rstd)
+    be.gn_stats(s1.to(DEV), None if s2 is None else s2.to(DEV), 32, 1e-5, m2, r2, ws)
+    assert torch.equal(mean, m2) and torch.equal(rstd, r2)          # deterministic
+
+
+@pytest.mark.parametrize("resample", [0, 1, 2])
+@pytest.mark.parametrize("c1,c2,film,silu", [(128, 0, True, True), (512, 128, False, True), (32, 0, True, True),
+                                              (64, 0, False, False), (1120, 0, False, True)])
+def test_prep_operand(be, resample, c1, c2, film, silu):
+    B, Hs, Ws = 2, 8, 12
+    C = c1 + c2
+    s1 = rnd((B, Hs, Ws, c1), 30)
+    s2 = rnd((B, Hs, Ws, c2), 31, 1.5) if c2 else None
+    x = s1 if s2 is None else torch.cat([s1, s2], 3)
+    mean, rstd = O.op_gn_stats(x)
+    gamma, beta = 1 + 0.1 * rnd((C,), 32), 0.1 * rnd((C,), 33)
+    fbuf = 0.2 * rnd((B, 3 * C + 8), 34)
+    fs, fh = (fbuf[:, 4:4 + C], fbuf[:, 4 + C:4 + 2 * C]) if film else (None, None)
+    want_act = O.op_gn_act(x.double(), mean.double(), rstd.double(), gamma.double(), beta.double(),
+                           None if fs is None else fs.double(), None if fh is None else fh.double(), silu, resample)
+    want_raw = O.op_resample(x, resample)
+    H, W = want_raw.shape[1:3]
+    d = lambda t: None if t is None else t.to(DEV)
+    act_f32, raw_f32 = torch.empty((B, H, W, C), device=DEV), torch.empty((B, H, W, C), device=DEV)
+    bf = lambda: torch.empty((B, H, W, C), dtype=torch.bfloat16, device=DEV)
+    act_hi, act_lo, raw_hi, raw_lo = bf(), bf(), bf(), bf()
+    fdev = d(fbuf)
+    be.prep(d(s1), d(s2), groups=32, mean=d(mean), rstd=d(rstd), gamma=d(gamma), beta=d(beta),
+            film_scale=None if not film else fdev[:, 4:4 + C], film_shift=None if not film else fdev[:, 4 + C:4 + 2 * C],
+            film_stride=fbuf.shape[1], silu=silu, resample=resample, act_f32=act_f32, act_hi=act_hi, act_lo=act_lo,
+            raw_f32=raw_f32, raw_hi=raw_hi, raw_lo=raw_lo)
+    assert rel_dev(act_f32, want_act) < 3e-6
+    assert rel_dev(raw_f32, want_raw) < 1e-6
+    # split planes: hi is exactly bf16(value), hi + lo reproduces the fp32 value to ~2^-17
+    hi, lo = O.bf16_split(act_f32.cpu())
+    assert torch.equal(act_hi.float().cpu(), hi) and torch.equal(act_lo.float().cpu(), lo)
+    hi, lo = O.bf16_split(raw_f32.cpu())
+    assert torch.equal(raw_hi.float().cpu(), hi) and torch.equal(raw_lo.float().cpu(), lo)
+    assert rel_dev(act_hi.float() + act_lo.float(), act_f32) < 2 ** -16
+
+
+# ------------------------------------------------------------------------------------ convolutions
+def _pack_split(be, w):
+    k = w.shape[-1]
+    hi = torch.empty((k * k, w.shape[0], w.shape[1]), dtype=torch.bfloat16, device=DEV)
+    lo = torch.empty_like(hi)
+    be.pack_weight_split(w.to(DEV).contiguous(), hi, lo)
+    return hi, lo
+
+
+def test_pack_weights(be):
+    w = rnd((128, 64, 3, 3), 40, 0.02)
+    hi, lo = _pack_split(be, w)
+    want = w.permute(2, 3, 0, 1).reshape(9, 128, 64)
+    h, l = O.bf16_split(want)
+    assert torch.equal(hi.float().cpu(), h) and torch.equal(lo.float().cpu(), l)
+    f = torch.empty((9, 64, 128), device=DEV)
+    be.pack_weight_f32(w.to(DEV), f)
+    assert torch.equal(f.cpu(), w.permute(2, 3, 1, 0).reshape(9, 64, 128))
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride", [(2, 16, 16, 6, 128, 3, 1), (2, 9, 11, 35, 3, 3, 1), (1, 16, 16, 128, 3, 3, 1),
+                                                      (2, 8, 8, 32, 96, 1, 1), (2, 16, 16, 32, 32, 3, 2), (3, 4, 4, 64, 200, 3, 1)])
+def test_conv_direct(be, B, H, W, Cin, Cout, k, stride):
+    a = rnd((B, H, W, Cin), 41)
+    w, b = rnd((Cout, Cin, k, k), 42, 0.05), rnd((Cout,), 43, 0.1)
+    want = torch.nn.functional.conv2d(a.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride=stride,
+                                      padding=k // 2).permute(0, 2, 3, 1)
+    res = rnd(tuple(want.shape), 44)
+    wp = torch.empty((k * k, Cin, Cout), device=DEV)
+    be.pack_weight_f32(w.to(DEV), wp)
+    out = torch.empty(tuple(want.shape), device=DEV)
+    be.conv_direct(a.to(DEV), wp, b.to(DEV), res.to(DEV), out, Cout, k, stride)
+    assert rel_dev(out, want + res.double()) < 3e-6
+
+
+CONV_CASES = [
+    # B, H,  W,  Cin, Cout, taps, Cin2, res_mode
+    (2, 16, 16, 64, 64, 9, 0, 0),        # smallest aligned case (BN=64)
+    (2, 16, 16, 128, 128, 9, 0, 1),      # BN=128 + same-res residual
+    (1, 32, 32, 128, 256, 9, 64, 0),     # BN=256 + fused 1x1 skip operand
+    (2, 8, 8, 256, 512, 9, 0, 2),        # TW=8 tile geometry, nearest-up residual
+    (2, 16, 16, 64, 128, 9, 0, 3),       # 2x2-avg residual
+    (3, 4, 4, 256, 256, 9, 0, 1),        # tile spans several images (TB=8 > B: OOB batch rows)
+    (2, 12, 20, 64, 64, 9, 0, 1),        # ragged: H, W not multiples of the box
+    (2, 16, 16, 128, 384, 1, 0, 1),      # 1x1 (qkv / proj_out shape), BN=128
+    (1, 64, 64, 640, 128, 9, 640, 0),    # output-block shape: concat width + 1x1 skip
+    (5, 16, 16, 1024, 1024, 9, 0, 1),    # K = 9216, many k-blocks, multiple tiles per CTA
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("passes", [3, 1])
+def test_conv_umma(be, case, passes):
+    B, H, W, Cin, Cout, taps, Cin2, res_mode = case
+    k = 3 if taps == 9 else 1
+    a = rnd((B, H, W, Cin), 50)
+    w, b = rnd((Cout, Cin, k, k), 51, 0.02), rnd((Cout,), 52, 0.1)
+    a_hi, a_lo = (t.to(torch.bfloat16).to(DEV) for t in O.bf16_split(a))
+    w_hi, w_lo = _pack_split(be, w)
+    kw = {}
+    d64 = torch.float64
+    if passes == 3:
+        want = O.op_conv_split3(a, w, b)
+    else:
+        want = O.op_conv_nhwc(O.bf16_split(a)[0].to(d64), O.bf16_split(w)[0].to(d64), b.to(d64))
+    if Cin2:
+        a2, w2, b2 = rnd((B, H, W, Cin2), 53), rnd((Cout, Cin2, 1, 1), 54, 0.02), rnd((Cout,), 55, 0.1)
+        a2_hi, a2_lo = (t.to(torch.bfloat16).to(DEV) for t in O.bf16_split(a2))
+        w2_hi, w2_lo = _pack_split(be, w2)
+        kw = dict(Cin2=Cin2, a2_hi=a2_hi, a2_lo=a2_lo, w2_hi=w2_hi, w2_lo=w2_lo, bias2=b2.to(DEV))
+        want = want + (O.op_conv_split3(a2, w2, b2) if passes == 3 else
+                       O.op_conv_nhwc(O.bf16_split(a2)[0].to(d64), O.bf16_split(w2)[0].to(d64), b2.to(d64)))
+    res = None
+    if res_mode == 1:
+        res = rnd((B, H, W, Cout), 56)
+        want = want + res.double()
+    elif res_mode == 2:
+        res = rnd((B, H // 2, W // 2, Cout), 56)
+        want = want + O.op_resample(res, 1).double()
+    elif res_mode == 3:
+        res = rnd((B, H * 2, W * 2, Cout), 56)
+        want = want + O.op_resample(res.double(), 2)
+    out = torch.full((B, H, W, Cout), float("nan"), device=DEV)
+    oh = torch.empty((B, H, W, Cout), dtype=torch.bfloat16, device=DEV)
+    ol = torch.empty_like(oh)
+    be.conv_umma(B=B, H=H, W=W, Cin=Cin, Cout=Cout, taps=taps, a_hi=a_hi, a_lo=a_lo, w_hi=w_hi, w_lo=w_lo,
+                 bias=b.to(DEV), residual=None if res is None else res.to(DEV), res_mode=res_mode, out=out,
+                 out_hi=oh, out_lo=ol, passes=passes, **kw)
+    torch.cuda.synchronize()
+    be.check_fault()
+    assert not torch.isnan(out).any()
+    # the kernel differs from the fp64 evaluation of the same split products only by fp32 accumulation
+    assert rel_dev(out, want) < 2e-6, rel_dev(out, want)
+    if passes == 3:      # and the split scheme itself is fp32-class accurate vs the exact conv
+        exact = O.op_conv_nhwc(a.double(), w.double(), b.double())
+        if Cin2 == 0 and res_mode == 0:
+            assert rel_dev(out, exact) < 3e-5
+    h, l = O.bf16_split(out.cpu())
+    assert torch.equal(oh.float().cpu(), h) and torch.equal(ol.float().cpu(), l)
+
+
+def test_conv_umma_rejects_bad_shapes(be):
+    from bbdm_b200.cabi import BbdmError
+    z = torch.zeros(8, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(BbdmError, match="Cin"):
+        be.conv_umma(B=1, H=8, W=8, Cin=48, Cout=64, taps=9, a_hi=z, a_lo=z, w_hi=z, w_lo=z, out=z)
+
+
+# ------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,T,heads,D,order", [(2, 256, 4, 64, 0), (1, 1024, 2, 64, 0), (2, 16, 8, 32, 0),
+                                                (2, 64, 4, 16, 1), (1, 100, 2, 64, 1), (2, 4096, 1, 64, 0)])
+def test_attention(be, B, T, heads, D, order):
+    C = heads * D
+    qkv = rnd((B, T, 3 * C), 60, 1.2)
+    want = O.op_attention_nhwc(qkv.double(), heads, bool(order))
+    out = torch.empty((B, T, C), device=DEV)
+    oh = torch.empty((B, T, C), dtype=torch.bfloat16, device=DEV)
+    ol = torch.empty_like(oh)
+    be.attention(qkv.to(DEV), heads, order, out_f32=out, out_hi=oh, out_lo=ol)
+    assert rel_dev(out, want) < 2e-5, rel_dev(out, want)
+    h, l = O.bf16_split(out.cpu())
+    assert torch.equal(oh.float().cpu(), h) and torch.equal(ol.float().cpu(), l)

@@ -1,0 +1,108 @@
+"""-m gpu: the drop-in model on the real kernels against the reference-generated fixtures
+(committed; /root/reference is not needed on the GPU box) and against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _recipe import UNET_CONFIGS, bb_namespace, fill_state_dict, rel_dev, synth_images
+from oracle import bbdm_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+# north_star tolerance: <= 1e-4 max relative deviation of p_sample output from the reference's
+TOL_PSAMPLE = 1e-4
+TAGS = {
+    "tiny_pixel": ("tiny_pixel", {}),
+    "tiny_latent": ("tiny_latent", dict(objective="noise", loss_type="l2")),
+    "tiny_variant": ("tiny_variant", dict(objective="ysubx", eta=0.5)),
+    "mid_pixel": ("mid_pixel", {}),
+    "cfg1": ("cfg1", dict(sample_step=100)),
+}
+
+
+def build(unet_name, **kw):
+    from model.BrownianBridge.BrownianBridgeModel import BrownianBridgeModel
+    net = BrownianBridgeModel(bb_namespace(UNET_CONFIGS[unet_name], **kw)).eval()
+    shapes = {k: tuple(v.shape) for k, v in net.denoise_fn.state_dict().items()}
+    net.denoise_fn.load_state_dict(fill_state_dict(shapes, seed=1234))
+    return net.to("cuda")
+
+
+def gold(tag):
+    p = os.path.join(GOLD, tag + ".npz")
+    if not os.path.exists(p):
+        pytest.skip(tag + ".npz missing")
+    return {k: torch.from_numpy(v) if v.ndim else v for k, v in np.load(p).items()}
+
+
+@pytest.mark.parametrize("tag", list(TAGS))
+def test_unet_and_p_sample_match_reference_fixture(tag):
+    unet_name, kw = TAGS[tag]
+    g = gold(tag)
+    net = build(unet_name, **kw)
+    c = lambda z: z.cuda()
+    x, y, t = c(g["x"]), c(g["y"]), c(g["t"])
+    ctx = None if net.condition_key == "nocond" else y
+    with torch.no_grad():
+        out = net.denoise_fn(x, timesteps=t, context=ctx)
+    d_unet = rel_dev(out, g["unet_out"])
+    xt, obj = net.q_sample(x, y, t, c(g["q_noise"]))
+    assert torch.equal(xt.cpu(), g["q_xt"]) and torch.equal(obj.cpu(), g["q_obj"])      # bit-exact
+    devs = {}
+    for i in g["ps_ids"].tolist():
+        for clip, key in ((False, f"ps{i}_out"), (True, f"ps{i}_out_clip")):
+            o, x0 = net.p_sample(c(g[f"ps{i}_xt"]), y, ctx, i, clip_denoised=clip, noise=c(g[f"ps{i}_noise"]))
+            devs[(i, clip)] = rel_dev(o, g[key])
+    net._bridge.backend().check_fault()
+    print(f"\n[{tag}] unet rel dev {d_unet:.3e}; p_sample rel dev {devs}")
+    assert d_unet < TOL_PSAMPLE
+    assert max(devs.values()) < TOL_PSAMPLE
+    if "loop8_out" in g:
+        net8 = build(unet_name, sample_step=8, **kw)
+        seq = iter(c(g["loop8_noise"]))
+        net8._bridge.noise_source = lambda like: next(seq)
+        img = net8.sample(y, clip_denoised=True)
+        d_loop = rel_dev(img, g["loop8_out"])
+        print(f"[{tag}] 8-step loop rel dev {d_loop:.3e}")
+        assert d_loop < (2e-3 if kw.get("objective") == "noise" else 2e-4)
+
+
+def test_training_step_on_gpu():
+    """forward -> loss -> backward on CUDA: fused q_sample kernel + autograd UNet graph."""
+    g = gold("tiny_pixel")
+    net = build("tiny_pixel").train()
+    x, y, t = g["x"].cuda(), g["y"].cuda(), g["t"].cuda()
+    loss, log = net.p_losses(x, y, y, t, g["q_noise"].cuda())
+    assert abs(float(loss) - float(g["loss"])) < 1e-3 * abs(float(g["loss"]))   # cuDNN may use TF32-free fp32
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.get_parameters())
+
+
+def test_sampling_is_deterministic_and_weights_refresh():
+    net = build("tiny_latent", sample_step=6)
+    y = synth_images((2, 4, 16, 16), 5).cuda()
+    torch.manual_seed(3)
+    a = net.sample(y, clip_denoised=False)
+    torch.manual_seed(3)
+    b = net.sample(y, clip_denoised=False)
+    assert torch.equal(a, b)
+    with torch.no_grad():
+        for p in net.denoise_fn.parameters():
+            p.mul_(1.01)                      # "optimizer step": caches must refresh
+    torch.manual_seed(3)
+    cimg = net.sample(y, clip_denoised=False)
+    assert not torch.equal(a, cimg)
+
+
+def test_bf16_fast_mode_is_close_but_not_parity():
+    g = gold("mid_pixel")
+    net = build("mid_pixel")
+    from bbdm_b200.engine import UNetEngine
+    eng = UNetEngine(net.denoise_fn, precision="bf16")
+    y = g["y"].cuda()
+    out = eng.forward(g["x"].cuda(), g["t"].cuda(), y)
+    d = rel_dev(out, g["unet_out"])
+    print(f"\n[mid_pixel] single-pass bf16 rel dev {d:.3e}")
+    assert 1e-4 < d < 5e-2
