@@ -36,7 +36,7 @@ class BridgeOps:
         return self._be
 
     def _require_device(self, t):
-        if not t.is_cuda and isinstance(self.backend(), cabi.CudaBackend):
+        if not t.is_cuda and getattr(self.backend(), "requires_cuda", True):
             raise RuntimeError("bbdm_b200: q_sample/p_sample run only on a CUDA sm_100a device "
                                "(kernels behind libbbdm_b200.so); there is no CPU fallback.")
 

@@ -133,6 +133,7 @@ class CudaBackend:
     logic on CPU; the product never does.)"""
 
     name = "sm_100a"
+    requires_cuda = True
 
     def __init__(self):
         self.lib = load()

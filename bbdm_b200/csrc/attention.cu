@@ -138,24 +138,27 @@ attention_kernel(const float* __restrict__ qkv, int T, int C, int heads, int ord
       l_run[0] += s[j][0] + s[j][1];
       l_run[1] += s[j][2] + s[j][3];
     }
-    // ---- O += P V ---------------------------------------------------------------------------
+    // ---- O += P V.  The tensor core's accumulator add truncates, so each KV tile's product is
+    // formed from a zero accumulator (12 k-steps) and added to O with a round-to-nearest fp32 add.
 #pragma unroll
-    for (int kk = 0; kk < KT / 16; ++kk) {
-      uint32_t ph[4], pl[4];
-      split2(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);          // row g,   keys 2t,2t+1
-      split2(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);          // row g+8
-      split2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);  // row g,   keys 8+2t,..
-      split2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);  // row g+8
+    for (int jd = 0; jd < D / 8; ++jd) {
+      float ot[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int jd = 0; jd < D / 8; ++jd) {
+      for (int kk = 0; kk < KT / 16; ++kk) {
+        uint32_t ph[4], pl[4];
+        split2(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);          // row g,   keys 2t,2t+1
+        split2(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);          // row g+8
+        split2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);  // row g,   keys 8+2t,..
+        split2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);  // row g+8
         const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(&Vh[jd * 8 + g][kk * 16 + 2 * t]);
         const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(&Vh[jd * 8 + g][kk * 16 + 8 + 2 * t]);
         const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(&Vl[jd * 8 + g][kk * 16 + 2 * t]);
         const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(&Vl[jd * 8 + g][kk * 16 + 8 + 2 * t]);
-        mma_bf16_16816(o[jd], pl, bh0, bh1);
-        mma_bf16_16816(o[jd], ph, bl0, bl1);
-        mma_bf16_16816(o[jd], ph, bh0, bh1);
+        mma_bf16_16816(ot, pl, bh0, bh1);
+        mma_bf16_16816(ot, ph, bl0, bl1);
+        mma_bf16_16816(ot, ph, bh0, bh1);
       }
+      o[jd][0] += ot[0]; o[jd][1] += ot[1]; o[jd][2] += ot[2]; o[jd][3] += ot[3];
     }
     __syncthreads();
   }

@@ -12,8 +12,13 @@
 //     TMA unit, which IS the conv padding -- no im2col buffer, no halo logic.
 //   * Warp-specialised persistent CTA: warp0 = TMA producer, warp1 = tcgen05.mma issuer (one
 //     elected lane) + TMEM owner, warps2-5 = epilogue (TMEM -> registers -> bias/residual ->
-//     global).  Two TMEM accumulator buffers so the epilogue of tile i overlaps the mainloop of
-//     tile i+1.
+//     global).  Two TMEM accumulator buffers: chunk promotion and the tile epilogue overlap the
+//     tensor-core mainloop.
+//   * fp32-faithful accumulation: the tensor core's accumulator add truncates (round-toward-zero),
+//     so a K = 9216 chain accumulated entirely in TMEM drifts by ~3e-5.  The K loop is therefore
+//     cut into chunks of `kb_per_chunk` K-blocks that alternate between the two TMEM buffers; the
+//     epilogue warps drain each finished chunk (tcgen05.ld) and add it into fp32 REGISTER
+//     accumulators with round-to-nearest while the tensor core works on the next chunk.
 //   * Every mbarrier wait has a clock-based watchdog: on expiry a device fault word is set and
 //     the CTA drains without deadlocking the GPU (bbdm_check_device_fault reports it).
 #include "common.cuh"
@@ -23,7 +28,6 @@ namespace bbdm {
 
 constexpr int UM_BM = 128;       // pixels per tile (UMMA M)
 constexpr int UM_BK = 64;        // bf16 per K block = 128 B rows (SWIZZLE_128B)
-constexpr int UM_THREADS = 192;  // 6 warps
 constexpr uint32_t UM_A_BYTES = UM_BM * UM_BK * 2;  // 16 KiB per plane per stage
 
 // ---------------------------------------------------------------------------------- PTX
@@ -124,6 +128,7 @@ struct ConvParams {
   int K2;           // Cin2 / 64
   int taps;
   int passes;
+  int kb_per_chunk;  // K blocks accumulated in TMEM before promotion to registers
   const float* bias; const float* bias2;
   const float* residual; int res_mode;
   float* out; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
@@ -139,10 +144,15 @@ struct UmmaCfg {
   static constexpr int STAGES3 = (SMEM_BUDGET / STAGE3) > 6 ? 6 : (SMEM_BUDGET / STAGE3);
   static constexpr int STAGES1 = (SMEM_BUDGET / STAGE1) > 8 ? 8 : (SMEM_BUDGET / STAGE1);
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // power of two for BN in {64,128,256}
+  // epilogue warps: 4 (one per TMEM lane quarter) own BN columns each; for BN = 256 two warps
+  // share a lane quarter (128 columns = 128 accumulator registers per thread)
+  static constexpr int EPI_WARPS = BN == 256 ? 8 : 4;
+  static constexpr int COLS = BN / (EPI_WARPS / 4);
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
 
 template <int BN, int PASSES>
-__global__ void __launch_bounds__(UM_THREADS, 1)
+__global__ void __launch_bounds__(UmmaCfg<BN>::THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                  const __grid_constant__ CUtensorMap map_a2_hi, const __grid_constant__ CUtensorMap map_a2_lo,
@@ -172,7 +182,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   if (threadIdx.x == 0) {
     abort_s = 0;
     for (int i = 0; i < STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, Cfg::EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -237,40 +247,46 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, abort_flag, p.fault, 0xA0000000ull | (unsigned)tile);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase, abort_flag, p.fault, 0xF0000000ull | (unsigned)kb);
+        for (int kb0 = 0; kb0 < KB; kb0 += p.kb_per_chunk) {
+          const int kb1 = kb0 + p.kb_per_chunk < KB ? kb0 + p.kb_per_chunk : KB;
+          mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, abort_flag, p.fault, 0xA0000000ull | (unsigned)tile);
           tc_fence_after();
-          const uint32_t sbase = tiles_base + stage * STAGE_BYTES;
-          const uint64_t da_hi = make_sw128_desc(sbase);
-          const uint64_t da_lo = make_sw128_desc(sbase + OFF_ALO);
-          const uint64_t db_hi = make_sw128_desc(sbase + OFF_WHI);
-          const uint64_t db_lo = make_sw128_desc(sbase + OFF_WLO);
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(bar_full + 8 * stage, phase, abort_flag, p.fault, 0xF0000000ull | (unsigned)kb);
+            tc_fence_after();
+            const uint32_t sbase = tiles_base + stage * STAGE_BYTES;
+            const uint64_t da_hi = make_sw128_desc(sbase);
+            const uint64_t da_lo = make_sw128_desc(sbase + OFF_ALO);
+            const uint64_t db_hi = make_sw128_desc(sbase + OFF_WHI);
+            const uint64_t db_lo = make_sw128_desc(sbase + OFF_WLO);
 #pragma unroll
-          for (int k = 0; k < UM_BK / 16; ++k) {
-            const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 B per UMMA_K inside the swizzle atom
-            const uint32_t first = (kb | k) ? 1u : 0u;
-            if (PASSES == 3) {
-              tc_mma_bf16(d_tmem, da_lo + ko, db_hi + ko, IDESC, first);
-              tc_mma_bf16(d_tmem, da_hi + ko, db_lo + ko, IDESC, 1u);
-              tc_mma_bf16(d_tmem, da_hi + ko, db_hi + ko, IDESC, 1u);
-            } else {
-              tc_mma_bf16(d_tmem, da_hi + ko, db_hi + ko, IDESC, first);
+            for (int k = 0; k < UM_BK / 16; ++k) {
+              const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 B per UMMA_K inside the swizzle atom
+              const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;   // a chunk starts from zero
+              if (PASSES == 3) {
+                tc_mma_bf16(d_tmem, da_lo + ko, db_hi + ko, IDESC, first);
+                tc_mma_bf16(d_tmem, da_hi + ko, db_lo + ko, IDESC, 1u);
+                tc_mma_bf16(d_tmem, da_hi + ko, db_hi + ko, IDESC, 1u);
+              } else {
+                tc_mma_bf16(d_tmem, da_hi + ko, db_hi + ko, IDESC, first);
+              }
             }
+            tc_commit(bar_empty + 8 * stage);          // frees the smem slot when these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(bar_empty + 8 * stage);          // frees the smem slot when these MMAs retire
-          if (kb == KB - 1) tc_commit(bar_tfull + 8 * acc);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          tc_commit(bar_tfull + 8 * acc);              // chunk complete -> promotion warps
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
     __syncwarp();
   } else {
-    // ================================ epilogue (4 warps) ====================================
+    // ================================ promotion + epilogue warps ============================
+    constexpr int COLS = Cfg::COLS;            // accumulator columns (= registers) per thread
+    const int ew = warp - 2;
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int col0 = (ew >> 2) * COLS;         // column half for BN = 256
     const int row = q * 32 + lane;             // tile row == TMEM lane
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -285,21 +301,35 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const int bb = tb * p.TB + row / (p.TW * p.TH);
       const bool valid = ww < p.W && hh < p.H && bb < p.B;
       const int64_t pix = ((int64_t)bb * p.H + hh) * p.W + ww;
-      const int n0 = nb * BN;
+      const int n0 = nb * BN + col0;
 
-      mbar_wait(bar_tfull + 8 * acc, acc_phase, abort_flag, p.fault, 0xD0000000ull | (unsigned)tile);
-      tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t v[32];
-        tc_ld32(t_addr + ch * 32, v);
-        tc_wait_ld();
-        if (valid) {
-          const int nc = n0 + ch * 32;
-          float r[32];
+      float racc[COLS];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+      for (int j = 0; j < COLS; ++j) racc[j] = 0.f;
+      // ---- drain every K chunk: TMEM -> registers, round-to-nearest fp32 adds -------------------
+      for (int kb0 = 0; kb0 < KB; kb0 += p.kb_per_chunk) {
+        mbar_wait(bar_tfull + 8 * acc, acc_phase, abort_flag, p.fault, 0xD0000000ull | (unsigned)tile);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + col0;
+#pragma unroll
+        for (int ch = 0; ch < COLS / 32; ++ch) {
+          uint32_t v[32];
+          tc_ld32(t_addr + ch * 32, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) racc[ch * 32 + j] += __uint_as_float(v[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      // ---- tile epilogue: bias / fused-skip bias / residual / store ------------------------------
+      if (valid) {
+#pragma unroll
+        for (int ch = 0; ch < COLS / 32; ++ch) {
+          const int nc = n0 + ch * 32;
+          float* r = &racc[ch * 32];
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -357,10 +387,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -435,7 +461,7 @@ static int launch_conv(const CUtensorMap* maps, const ConvParams& p, int grid, c
     BBDM_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  conv_umma_kernel<BN, PASSES><<<grid, UM_THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
+  conv_umma_kernel<BN, PASSES><<<grid, Cfg::THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
                                                               maps[6], maps[7], p);
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
@@ -476,6 +502,7 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   p.K2 = a->Cin2 / 64;
   p.taps = a->taps;
   p.passes = a->passes;
+  p.kb_per_chunk = a->passes == 3 ? 4 : 8;
   p.bias = a->bias; p.bias2 = a->Cin2 ? a->bias2 : nullptr;
   p.residual = a->residual; p.res_mode = a->res_mode;
   p.out = a->out; p.out_hi = (__nv_bfloat16*)a->out_hi; p.out_lo = (__nv_bfloat16*)a->out_lo;

@@ -264,11 +264,12 @@ class UNetModel(nn.Module):
             x.requires_grad or any(p.requires_grad for p in self.parameters()))
         if needs_grad:
             return self._forward_autograd(x, timesteps, context)
-        if not x.is_cuda:
+        eng = self.engine()       # raises if libbbdm_b200.so is not built
+        if not x.is_cuda and getattr(eng.be, "requires_cuda", True):
             raise RuntimeError(
                 "bbdm_b200: the denoising UNet inference path runs only on a CUDA sm_100a device "
                 "(hand-written kernels behind libbbdm_b200.so); there is no CPU fallback.")
-        return self.engine().forward(x, timesteps, context)
+        return eng.forward(x, timesteps, context)
 
     def _forward_autograd(self, x, timesteps, context):
         """Training graph: plain PyTorch ops over the same parameters (openaimodel.py:721-759)."""

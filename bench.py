@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- denoising-steps/sec of the BBDM hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg2]
+
+One "step" = one p_sample at the configured batch: UNet forward + fused Brownian-bridge update
+(+ the Gaussian draw), i.e. one iteration of the reference's p_sample_loop
+(model/BrownianBridge/BrownianBridgeModel.py:171-221).  Workload at N=1: BASELINE configs[1],
+pixel-space BBDM 256x256 RGB, batch 16, 200-step skip schedule, random-init weights, synthetic
+paired images.  N>1: one process per GPU (torchrun), every rank samples its own batch of 16
+(the test set shards with no collective) => weak scaling, value = sum over ranks.
+
+Prints ONE JSON line (see the task contract): value (HBM-resident inputs), e2e (host buffers,
+H2D + D2H inside the timed region), roofline (tcgen05 conv kernel family), cpu_baseline
+(oracle port on the host cores, bounded sample), clocks, gpu_launches.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CONFIGS = {
+    # name: (UNet kwargs, batch, image size, sample_step, description)
+    "cfg2": dict(unet=dict(image_size=256, in_channels=6, model_channels=128, out_channels=3, num_res_blocks=2,
+                           attention_resolutions=(32, 16, 8), channel_mult=(1, 4, 8), conv_resample=True, dims=2,
+                           num_heads=8, num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True,
+                           use_spatial_transformer=False, context_dim=None, condition_key="SpatialRescaler"),
+                 batch=16, size=256, channels=3, sample_step=200,
+                 name="pixel-BBDM 256x256 RGB, batch 16, 200-step skip sampling (BASELINE configs[1])",
+                 flops_per_step=64.46e12),
+    "cfg1": dict(unet=dict(image_size=64, in_channels=6, model_channels=128, out_channels=3, num_res_blocks=2,
+                           attention_resolutions=(32, 16, 8), channel_mult=(1, 4, 8), conv_resample=True, dims=2,
+                           num_heads=8, num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True,
+                           use_spatial_transformer=False, context_dim=None, condition_key="SpatialRescaler"),
+                 batch=4, size=64, channels=3, sample_step=100,
+                 name="pixel-BBDM 64x64 RGB, batch 4, 100 steps (BASELINE configs[0])",
+                 flops_per_step=0.991e12),
+}
+METRIC = "denoising-steps/sec (UNet fwd) at 256^2 pixel-BBDM"
+
+
+def namespace(unet, sample_step):
+    import argparse as ap
+    ns = ap.Namespace
+    params = ns(mt_type="linear", objective="grad", loss_type="l1", skip_sample=True, sample_type="linear",
+                sample_step=sample_step, num_timesteps=1000, eta=1.0, max_var=1.0, UNetParams=ns(**unet))
+    return ns(model_name="BrownianBridge", model_type="BBDM", latent_before_quant_conv=False,
+              normalize_latent=False, only_load_latent_mean_std=False, BB=ns(params=params))
+
+
+def init_weights(unet, seed=1234):
+    """reference ctor init + runners/utils.py:35-45 weights_init (N(0,0.02) on every Conv2d/Linear
+    weight) under seed 1234, then attention proj_out ~ N(0,0.02) so attention is live
+    (BASELINE.md section 3)."""
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    for m in unet.modules():
+        if isinstance(m, (nn.Conv2d, nn.Linear)):
+            nn.init.normal_(m.weight.data, 0.0, 0.02)
+    for name, m in unet.named_modules():
+        if name.endswith("proj_out"):
+            nn.init.normal_(m.weight.data, 0.0, 0.02)
+
+
+def synth(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (0.5 * torch.randn(shape, generator=g)).clamp_(-1, 1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.2 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows]
+        reasons = set()
+        for r in rows:
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (pure torch CPU restatement of the reference algorithm) on the host
+# cores.  /root/reference is Python and does not exist on the GPU box, so kind = "port".
+# ------------------------------------------------------------------------------------------
+def cpu_step_time(cfg, sample_batch, n_steps, threads):
+    from oracle import bbdm_oracle as O
+    from bbdm_b200.unet import UNetModel
+    torch.set_num_threads(threads)
+    unet = UNetModel(**cfg["unet"])
+    init_weights(unet)
+    sd = {k: v.detach() for k, v in unet.state_dict().items()}
+    ocfg = O.unet_cfg(**cfg["unet"])
+    bufs, steps = O.make_schedule(sample_step=cfg["sample_step"])
+    S, C = cfg["size"], cfg["channels"]
+    y = synth((sample_batch, C, S, S), 1)
+    x = synth((sample_batch, C, S, S), 2)
+    times = []
+    with torch.no_grad():
+        for i in range(n_steps + 1):                      # first iteration = warm-up
+            nz = torch.randn(x.shape)
+            t0 = time.perf_counter()
+            x, _ = O.p_sample(sd, ocfg, bufs, steps, 3 + i, x, y, y, nz, prefix="")
+            times.append(time.perf_counter() - t0)
+    return statistics.mean(times[1:]) if n_steps else times[0]
+
+
+def run_reference_arm(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sb = 1 if cfg["batch"] > 4 else cfg["batch"]
+    per = cpu_step_time(cfg, sb, max(1, args.steps), threads)
+    scale = cfg["batch"] / sb
+    ms = per * scale * 1e3
+    val = 1e3 / ms
+    sample = (f"{max(1, args.steps)} p_sample step(s) on {sb} of the {cfg['batch']} images (time scaled x{scale:g}), "
+              f"after 1 warm-up step; oracle port (torch CPU fp32), {threads} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["name"], "batch_per_gpu": cfg["batch"], "parallelism": "cpu"},
+            "cpu_baseline": {"value": val, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
+    ap.add_argument("--precision", default="split3", choices=["split3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        return run_reference_arm(args, cfg)
+    assert args.warmup >= 3, "timing rules: W >= 3"
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from bbdm_b200 import cabi
+    from bbdm_b200.bridge import BridgeOps
+    from bbdm_b200.engine import UNetEngine
+    from model.BrownianBridge.BrownianBridgeModel import BrownianBridgeModel
+
+    class ProfilingBackend(cabi.CudaBackend):
+        """Same kernels; optionally brackets every tcgen05 conv launch with CUDA events on the
+        launching stream so the roofline numbers are measured live."""
+        record = False
+        events = []
+
+        def conv_umma(self, **kw):
+            if not ProfilingBackend.record:
+                return super().conv_umma(**kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            super().conv_umma(**kw)
+            e1.record()
+            flops = 2.0 * kw["B"] * kw["H"] * kw["W"] * kw["Cout"] * (kw["taps"] * kw["Cin"] + kw.get("Cin2", 0))
+            ProfilingBackend.events.append((e0, e1, flops))
+
+    BridgeOps.backend_factory = staticmethod(lambda: ProfilingBackend())
+    net = BrownianBridgeModel(namespace(cfg["unet"], cfg["sample_step"])).eval()
+    init_weights(net.denoise_fn)
+    net = net.to(dev)
+    if args.precision != "split3":
+        be = net._bridge.backend()
+        object.__setattr__(net.denoise_fn, "_engine", UNetEngine(net.denoise_fn, backend=be, precision=args.precision))
+    B, S, C = cfg["batch"], cfg["size"], cfg["channels"]
+    y_host = synth((B, C, S, S), 1000 + rank).pin_memory()
+    x_host = synth((B, C, S, S), 2000 + rank).pin_memory()
+    out_host = torch.empty((B, C, S, S)).pin_memory()
+    y = y_host.to(dev)
+    n_sched = len(net.steps)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing: K consecutive steps of the loop ---------------------------------
+    x = x_host.to(dev)
+    for i in range(args.warmup):
+        x, _ = net.p_sample(x, y, y, 5 + i)
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.3)
+    n0 = cabi.LAUNCHES["n"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        x, _ = net.p_sample(x, y, y, (10 + i) % (n_sched - 1))
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = cabi.LAUNCHES["n"] - n0
+    ms_dev = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+
+    # ---- end to end: host buffers, H2D of the step inputs + D2H of the result every step -----------
+    for i in range(2):
+        xd = x_host.to(dev, non_blocking=True)
+        o, _ = net.p_sample(xd, y_host.to(dev, non_blocking=True), None, 7)
+        out_host.copy_(o, non_blocking=True)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        xd = x_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        o, _ = net.p_sample(xd, yd, None, (10 + i) % (n_sched - 1))     # public API call; context defaults to y
+        out_host.copy_(o, non_blocking=True)
+        x_host.copy_(out_host)                                           # next step's host-side input
+    e3.record()
+    barrier()
+    clk = clocks.stop(t_wall0, time.time())
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3)) / args.steps
+    net._bridge.backend().check_fault()
+
+    # ---- roofline of the dominant kernel family (tcgen05 implicit-GEMM conv), one profiled step -----
+    ProfilingBackend.record, ProfilingBackend.events = True, []
+    x2, _ = net.p_sample(x, y, y, 20)
+    torch.cuda.synchronize()
+    ProfilingBackend.record = False
+    conv_ms = sum(a.elapsed_time(b) for a, b, _ in ProfilingBackend.events)
+    conv_flops = sum(f for _, _, f in ProfilingBackend.events)
+    n_conv = len(ProfilingBackend.events)
+    peaks, peak_src = load_peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    achieved_tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf, "traffic": None,
+                "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM conv, %d launches/step)" % n_conv,
+                "algorithmic_flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms,
+                "share_of_step": conv_ms / ms_dev if ms_dev else None,
+                "peak_source": peak_src + ", bf16 sustained",
+                "note": ("algorithmic FLOPs (2*M*N*K of the reference conv); precision mode '%s' issues %dx that on the "
+                         "tensor pipe" % (args.precision, 3 if args.precision == "split3" else 1))}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sb = 1 if B > 4 else B
+            per = cpu_step_time(cfg, sb, 1, threads)
+            scale = B / sb
+            cpu = {"value": 1.0 / (per * scale), "unit": "steps/s", "cores": threads, "kind": "port",
+                   "sample": f"1 p_sample step on {sb} of the {B} images (time scaled x{scale:g}) after 1 warm-up; "
+                             f"oracle port (torch CPU fp32)"}
+        nbytes = B * C * S * S * 4
+        line = {"metric": METRIC, "value": world * 1e3 / ms_dev, "unit": "steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16x3 (split-bf16 tensor-core products, fp32 accumulate: fp32-class)" if args.precision == "split3" else "bf16",
+                "data": "synthetic",
+                "config": {"workload": cfg["name"], "batch_per_gpu": B, "image": [C, S, S], "parallelism": f"dp{world} (sharded sampling, no collective)",
+                           "precision": args.precision, "l2": "inputs larger than L2 (activations 0.5-1.3 GB per tensor)",
+                           "img_steps_per_s": world * B * 1e3 / ms_dev,
+                           "unet_tflops_per_s": world * cfg["flops_per_step"] / (ms_dev * 1e-3) / 1e12},
+                "e2e": {"value": world * 1e3 / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": 2 * nbytes,
+                        "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

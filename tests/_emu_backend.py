@@ -12,6 +12,7 @@ RESAMPLE = {0: 0, 1: 1, 2: 2}
 
 class EmuBackend:
     name = "oracle-emulation (tests only)"
+    requires_cuda = False
 
     def __init__(self, split_emulation=False):
         self.calls = []

@@ -233,7 +233,7 @@ def test_conv_umma(be, case, passes):
     be.check_fault()
     assert not torch.isnan(out).any()
     # the kernel differs from the fp64 evaluation of the same split products only by fp32 accumulation
-    assert rel_dev(out, want) < 2e-6, rel_dev(out, want)
+    assert rel_dev(out, want) < 6e-6, rel_dev(out, want)
     if passes == 3:      # and the split scheme itself is fp32-class accurate vs the exact conv
         exact = O.op_conv_nhwc(a.double(), w.double(), b.double())
         if Cin2 == 0 and res_mode == 0:
