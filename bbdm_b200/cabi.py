@@ -23,7 +23,7 @@ GN_MAX_SLICES = 64
 # every symbol include/bbdm_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "bbdm_abi_version", "bbdm_last_error", "bbdm_device_info", "bbdm_check_device_fault",
-    "bbdm_bridge_q_sample", "bbdm_bridge_p_sample", "bbdm_nchw_to_nhwc_cat", "bbdm_nhwc_to_nchw",
+    "bbdm_bridge_q_sample", "bbdm_bridge_p_sample", "bbdm_bridge_p_sample_dev", "bbdm_nchw_to_nhwc_cat", "bbdm_nhwc_to_nchw",
     "bbdm_gather_rows", "bbdm_linear_f32", "bbdm_gn_stats", "bbdm_prep_operand",
     "bbdm_pack_weight_split", "bbdm_pack_weight_f32", "bbdm_conv_umma", "bbdm_conv_direct",
     "bbdm_attention",
@@ -83,6 +83,7 @@ def load():
     lib.bbdm_check_device_fault.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     lib.bbdm_bridge_q_sample.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp, vp, i, i64, vp]
     lib.bbdm_bridge_p_sample.argtypes = [vp, vp, vp, vp, PSampleCoef, i, i, i, vp, vp, i64, vp]
+    lib.bbdm_bridge_p_sample_dev.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp, vp, i64, vp]
     lib.bbdm_nchw_to_nhwc_cat.argtypes = [vp, i, vp, i, i, i, i, vp, vp]
     lib.bbdm_nhwc_to_nchw.argtypes = [vp, i, i, i, i, vp, vp]
     lib.bbdm_gather_rows.argtypes = [vp, i, i, vp, i, vp, vp]
@@ -161,6 +162,14 @@ class CudaBackend:
         check(self.lib.bbdm_bridge_p_sample(ptr(x_t), ptr(y), ptr(eps), ptr(noise), c, OBJ[objective],
                                             int(clip), int(is_last), ptr(x_out), ptr(x0_out), x_t.numel(),
                                             stream()))
+        LAUNCHES["n"] += 1
+
+    def p_sample_dev(self, x_t, y, eps, noise, coef_dev, objective, clip, is_last, x_out, x0_out):
+        for z in (x_t, y, eps, x_out, coef_dev):
+            _req(z)
+        check(self.lib.bbdm_bridge_p_sample_dev(ptr(x_t), ptr(y), ptr(eps), ptr(noise), ptr(coef_dev),
+                                                OBJ[objective], int(clip), int(is_last), ptr(x_out), ptr(x0_out),
+                                                x_t.numel(), stream()))
         LAUNCHES["n"] += 1
 
     # -- layout / dense ----------------------------------------------------------------------

@@ -46,7 +46,9 @@ template <int OBJ, bool CLIP, bool LAST>
 __global__ void __launch_bounds__(256)
 p_sample_kernel(const float4* __restrict__ xt, const float4* __restrict__ y,
                 const float4* __restrict__ eps, const float4* __restrict__ nz,
-                BbdmPSampleCoef c, float4* __restrict__ out, float4* __restrict__ x0o, int64_t n4) {
+                BbdmPSampleCoef c, const BbdmPSampleCoef* __restrict__ c_dev, float4* __restrict__ out,
+                float4* __restrict__ x0o, int64_t n4) {
+  if (c_dev) c = *c_dev;   // per-step scalars from device memory (CUDA-graph replay of the loop)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (int64_t)gridDim.x * blockDim.x) {
     const float4 X = xt[i], Y = y[i], E = eps[i];
@@ -220,9 +222,10 @@ int bbdm_bridge_q_sample(const float* x0, const float* y, const float* noise, co
   return BBDM_OK;
 }
 
-int bbdm_bridge_p_sample(const float* x_t, const float* y, const float* eps, const float* noise,
-                         BbdmPSampleCoef coef, int objective, int clip_denoised, int is_last,
-                         float* x_out, float* x0_out, int64_t n, void* stream) {
+static int p_sample_launch(const float* x_t, const float* y, const float* eps, const float* noise,
+                           BbdmPSampleCoef coef, const BbdmPSampleCoef* coef_dev, int objective,
+                           int clip_denoised, int is_last, float* x_out, float* x0_out, int64_t n,
+                           void* stream) {
   BBDM_REQUIRE(x_t && y && eps && x_out, "p_sample: null pointer");
   BBDM_REQUIRE(is_last || noise, "p_sample: noise required unless is_last");
   BBDM_REQUIRE(n > 0 && n % 4 == 0, "p_sample: n %% 4 != 0");
@@ -233,7 +236,7 @@ int bbdm_bridge_p_sample(const float* x_t, const float* y, const float* eps, con
 #define BBDM_PL(O, C, L)                                                                     \
   p_sample_kernel<O, C, L><<<grid, 256, 0, s>>>((const float4*)x_t, (const float4*)y,       \
                                                 (const float4*)eps, (const float4*)noise, coef, \
-                                                (float4*)x_out, (float4*)x0_out, n4)
+                                                coef_dev, (float4*)x_out, (float4*)x0_out, n4)
 #define BBDM_PL2(O)                                      \
   if (clip_denoised) { if (is_last) BBDM_PL(O, true, true); else BBDM_PL(O, true, false); } \
   else { if (is_last) BBDM_PL(O, false, true); else BBDM_PL(O, false, false); }
@@ -244,6 +247,20 @@ int bbdm_bridge_p_sample(const float* x_t, const float* y, const float* eps, con
 #undef BBDM_PL
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
+}
+
+int bbdm_bridge_p_sample(const float* x_t, const float* y, const float* eps, const float* noise,
+                         BbdmPSampleCoef coef, int objective, int clip_denoised, int is_last,
+                         float* x_out, float* x0_out, int64_t n, void* stream) {
+  return p_sample_launch(x_t, y, eps, noise, coef, nullptr, objective, clip_denoised, is_last, x_out, x0_out, n, stream);
+}
+
+int bbdm_bridge_p_sample_dev(const float* x_t, const float* y, const float* eps, const float* noise,
+                             const BbdmPSampleCoef* coef_dev, int objective, int clip_denoised,
+                             int is_last, float* x_out, float* x0_out, int64_t n, void* stream) {
+  BBDM_REQUIRE(coef_dev != nullptr, "p_sample_dev: null coefficient pointer");
+  BbdmPSampleCoef z = {0, 0, 0, 0, 0, 0, 0};
+  return p_sample_launch(x_t, y, eps, noise, z, coef_dev, objective, clip_denoised, is_last, x_out, x0_out, n, stream);
 }
 
 int bbdm_nchw_to_nhwc_cat(const float* x, int c1, const float* ctx, int c2, int B, int H, int W,

@@ -60,10 +60,15 @@ class UNetEngine:
         self._table = None
         self._gn_ws = None
         self.num_timesteps = 1000
+        self.generation = 0          # bumps whenever cache/parameter ADDRESSES change (graphs key on it)
 
     # ------------------------------------------------------------------------------ weights
     def _params_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.unet.parameters())
+
+    @staticmethod
+    def _ptrs(key):
+        return None if key is None else tuple(k[0] for k in key)
 
     def _umma_ok(self, cin, cout, w):
         return cin % 64 == 0 and cout % 64 == 0 and w >= 4
@@ -76,7 +81,18 @@ class UNetEngine:
             return
         be, u = self.be, self.unet
         dev = next(u.parameters()).device
+        # same parameter storage (in-place optimizer update): re-pack into the existing cache
+        # buffers so their addresses -- and any captured CUDA graph -- stay valid
+        old = self._w if (self._ptrs(key) == self._ptrs(self._wkey) and self._w) else {}
+        if not old:
+            self.generation += 1
         w = {}
+
+        def buf(name, field, shape, dtype):
+            t = old.get(name, {}).get(field) if isinstance(old.get(name), dict) else None
+            if t is not None and tuple(t.shape) == tuple(shape) and t.device == dev:
+                return t
+            return be.empty(tuple(shape), dtype, dev)
 
         def pack(conv, name):
             wt = conv.weight.detach()
@@ -86,11 +102,11 @@ class UNetEngine:
             cout, cin, k = wt.shape[0], wt.shape[1], wt.shape[2]
             ent = {"cout": cout, "cin": cin, "k": k, "bias": conv.bias.detach() if conv.bias is not None else None}
             if cin % 64 == 0 and cout % 64 == 0 and k in (1, 3):
-                hi = be.empty((k * k, cout, cin), torch.bfloat16, dev)
-                lo = be.empty((k * k, cout, cin), torch.bfloat16, dev)
+                hi = buf(name, "hi", (k * k, cout, cin), torch.bfloat16)
+                lo = buf(name, "lo", (k * k, cout, cin), torch.bfloat16)
                 be.pack_weight_split(wt, hi, lo)
                 ent["hi"], ent["lo"] = hi, lo
-            f32 = be.empty((k * k, cin, cout), torch.float32, dev)
+            f32 = buf(name, "f32", (k * k, cin, cout), torch.float32)
             be.pack_weight_f32(wt, f32)
             ent["f32"] = f32
             w[name] = ent
@@ -112,8 +128,13 @@ class UNetEngine:
                 film_b.append(b)
                 w[name + "#film"] = (off, n)
                 off += n
-        w["film_w"] = torch.cat(film_w, 0).contiguous()
-        w["film_b"] = torch.cat(film_b, 0).contiguous()
+        if old and old.get("film_n") == off:
+            w["film_w"], w["film_b"] = old["film_w"], old["film_b"]
+            torch.cat(film_w, 0, out=w["film_w"])
+            torch.cat(film_b, 0, out=w["film_b"])
+        else:
+            w["film_w"] = torch.cat(film_w, 0).contiguous()
+            w["film_b"] = torch.cat(film_b, 0).contiguous()
         w["film_n"] = off
         self._w = w
         self._wkey = key

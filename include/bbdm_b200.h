@@ -76,6 +76,13 @@ int bbdm_bridge_p_sample(const float* x_t, const float* y, const float* eps, con
                          BbdmPSampleCoef coef, int objective, int clip_denoised, int is_last,
                          float* x_out, float* x0_out, int64_t n, void* stream);
 
+/* Same, with the coefficient struct read from DEVICE memory at kernel start, so one captured
+ * CUDA graph of (UNet forward + this update) serves every non-final step of p_sample_loop
+ * (BrownianBridgeModel.py:203-221): the host only rewrites 7 floats + the timestep per step. */
+int bbdm_bridge_p_sample_dev(const float* x_t, const float* y, const float* eps, const float* noise,
+                             const BbdmPSampleCoef* coef_dev, int objective, int clip_denoised,
+                             int is_last, float* x_out, float* x0_out, int64_t n, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Layout / small dense ops
  * ------------------------------------------------------------------------------------------ */

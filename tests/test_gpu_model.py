@@ -106,3 +106,29 @@ def test_bf16_fast_mode_is_close_but_not_parity():
     d = rel_dev(out, g["unet_out"])
     print(f"\n[mid_pixel] single-pass bf16 rel dev {d:.3e}")
     assert 1e-4 < d < 5e-2
+
+
+def test_cuda_graph_loop_equals_eager_loop():
+    """p_sample_loop replays one captured step graph; it must reproduce the eager loop bit for bit,
+    survive an in-place weight update (caches re-packed in place) and an EMA-style .data swap."""
+    net = build("mid_pixel", sample_step=6)
+    y = synth_images((2, 3, 32, 32), 9).cuda()
+
+    def run(graph):
+        net._bridge.use_cuda_graph = graph
+        torch.manual_seed(11)
+        return net.sample(y, clip_denoised=True)
+
+    a, b = run(False), run(True)
+    assert torch.equal(a, b)
+    assert torch.equal(run(True), b)                       # replay again
+    with torch.no_grad():
+        for p in net.denoise_fn.parameters():
+            p.mul_(1.02)                                   # optimizer-style in-place step
+    a2, b2 = run(False), run(True)
+    assert torch.equal(a2, b2) and not torch.equal(a2, a)
+    for p in net.denoise_fn.parameters():
+        p.data = p.data.clone() * 0.99                      # EMA-style storage swap -> re-capture
+    a3, b3 = run(False), run(True)
+    assert torch.equal(a3, b3) and not torch.equal(a3, a2)
+    net._bridge.backend().check_fault()
