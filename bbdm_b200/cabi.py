@@ -25,8 +25,8 @@ SYMBOLS = [
     "bbdm_abi_version", "bbdm_last_error", "bbdm_device_info", "bbdm_check_device_fault",
     "bbdm_bridge_q_sample", "bbdm_bridge_p_sample", "bbdm_bridge_p_sample_dev", "bbdm_nchw_to_nhwc_cat", "bbdm_nhwc_to_nchw",
     "bbdm_gather_rows", "bbdm_linear_f32", "bbdm_gn_stats", "bbdm_prep_operand",
-    "bbdm_pack_weight_split", "bbdm_pack_weight_f32", "bbdm_conv_umma", "bbdm_conv_direct",
-    "bbdm_attention",
+    "bbdm_pack_weight_split", "bbdm_pack_weight_split_padded", "bbdm_pack_weight_f32", "bbdm_conv_umma", "bbdm_conv_direct",
+    "bbdm_attention", "bbdm_attention_split",
 ]
 
 
@@ -56,7 +56,7 @@ class ConvArgs(C.Structure):
                 ("bias2", C.c_void_p),
                 ("residual", C.c_void_p), ("res_mode", C.c_int),
                 ("out", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
-                ("passes", C.c_int)]
+                ("passes", C.c_int), ("out_nchw_channels", C.c_int)]
 
 
 class BbdmError(RuntimeError):
@@ -91,10 +91,12 @@ def load():
     lib.bbdm_gn_stats.argtypes = [vp, i, vp, i, i, i, i, i, f, vp, vp, vp, vp]
     lib.bbdm_prep_operand.argtypes = [C.POINTER(PrepArgs), vp]
     lib.bbdm_pack_weight_split.argtypes = [vp, i, i, i, vp, vp, vp]
+    lib.bbdm_pack_weight_split_padded.argtypes = [vp, i, i, i, i, vp, vp, vp]
     lib.bbdm_pack_weight_f32.argtypes = [vp, i, i, i, vp, vp]
     lib.bbdm_conv_umma.argtypes = [C.POINTER(ConvArgs), vp]
     lib.bbdm_conv_direct.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
     lib.bbdm_attention.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp]
+    lib.bbdm_attention_split.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp]
     for s in SYMBOLS:
         fn = getattr(lib, s)
         if s not in ("bbdm_last_error",):
@@ -217,8 +219,10 @@ class CudaBackend:
 
     # -- convolutions --------------------------------------------------------------------------
     def pack_weight_split(self, w, hi, lo):
+        """hi/lo: [k*k, Cout_pad, Cin] bf16 (Cout_pad >= Cout; padding rows must already be zero)."""
         Cout, Cin, k = w.shape[0], w.shape[1], (w.shape[2] if w.dim() > 2 else 1)
-        check(self.lib.bbdm_pack_weight_split(ptr(_req(w)), Cout, Cin, k, ptr(hi), ptr(lo), stream()))
+        check(self.lib.bbdm_pack_weight_split_padded(ptr(_req(w)), Cout, Cin, k, hi.shape[1], ptr(hi), ptr(lo),
+                                                     stream()))
         LAUNCHES["n"] += 1
 
     def pack_weight_f32(self, w, out):
@@ -228,10 +232,10 @@ class CudaBackend:
 
     def conv_umma(self, *, B, H, W, Cin, Cout, taps, a_hi, a_lo, w_hi, w_lo, bias=None, Cin2=0,
                   a2_hi=None, a2_lo=None, w2_hi=None, w2_lo=None, bias2=None, residual=None,
-                  res_mode=RES_NONE, out=None, out_hi=None, out_lo=None, passes=3):
+                  res_mode=RES_NONE, out=None, out_hi=None, out_lo=None, passes=3, out_nchw_channels=0):
         a = ConvArgs(B, H, W, Cin, Cout, taps, ptr(a_hi), ptr(a_lo), ptr(w_hi), ptr(w_lo), ptr(bias),
                      Cin2, ptr(a2_hi), ptr(a2_lo), ptr(w2_hi), ptr(w2_lo), ptr(bias2),
-                     ptr(residual), res_mode, ptr(out), ptr(out_hi), ptr(out_lo), passes)
+                     ptr(residual), res_mode, ptr(out), ptr(out_hi), ptr(out_lo), passes, out_nchw_channels)
         check(self.lib.bbdm_conv_umma(C.byref(a), stream()))
         LAUNCHES["n"] += 1
 
@@ -246,6 +250,13 @@ class CudaBackend:
         B, T, C3 = qkv.shape
         check(self.lib.bbdm_attention(ptr(_req(qkv)), B, T, C3 // 3, heads, order, ptr(out_f32),
                                       ptr(out_hi), ptr(out_lo), stream()))
+        LAUNCHES["n"] += 1
+
+    def attention_split(self, qkv_hi, qkv_lo, heads, order, out_f32=None, out_hi=None, out_lo=None):
+        B, T, C3 = qkv_hi.shape
+        check(self.lib.bbdm_attention_split(ptr(_req(qkv_hi, torch.bfloat16)), ptr(_req(qkv_lo, torch.bfloat16)),
+                                            B, T, C3 // 3, heads, order, ptr(out_f32), ptr(out_hi), ptr(out_lo),
+                                            stream()))
         LAUNCHES["n"] += 1
 
     def check_fault(self):

@@ -132,6 +132,7 @@ struct ConvParams {
   const float* bias; const float* bias2;
   const float* residual; int res_mode;
   float* out; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+  int out_nchw_c;    // > 0: out is NCHW with this many channels (UNet head)
   unsigned long long* fault;
 };
 
@@ -371,7 +372,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               r[j + 3] += 0.25f * (((t0.w + t1.w) + t2.w) + t3.w);
             }
           }
-          if (p.out) {
+          if (p.out_nchw_c > 0) {
+            // head: first out_nchw_c couts straight into the NCHW result (lanes = consecutive w)
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nc + j < p.out_nchw_c)
+                p.out[(((int64_t)bb * p.out_nchw_c + nc + j) * p.H + hh) * p.W + ww] = r[j];
+          } else if (p.out) {
             float* op = p.out + pix * p.Cout + nc;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) st_f4(op + j, make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]));
@@ -506,6 +513,9 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   p.bias = a->bias; p.bias2 = a->Cin2 ? a->bias2 : nullptr;
   p.residual = a->residual; p.res_mode = a->res_mode;
   p.out = a->out; p.out_hi = (__nv_bfloat16*)a->out_hi; p.out_lo = (__nv_bfloat16*)a->out_lo;
+  p.out_nchw_c = a->out_nchw_channels;
+  BBDM_REQUIRE(p.out_nchw_c >= 0 && p.out_nchw_c <= a->Cout && (p.out_nchw_c == 0 || (a->out && !a->out_hi)),
+               "conv_umma: bad out_nchw_channels");
   p.fault = device_fault_ptr();
   BBDM_REQUIRE(p.fault != nullptr, "conv_umma: device fault word unavailable");
 

@@ -158,7 +158,7 @@ linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
 // Weight repacking: OIHW fp32 -> [tap][Cout][Cin] split bf16 / [tap][Cin][Cout] fp32
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-pack_weight_split_kernel(const float* __restrict__ w, int Cout, int Cin, int kk,
+pack_weight_split_kernel(const float* __restrict__ w, int Cout, int Cin, int kk, int Cout_pad,
                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   const int64_t n = (int64_t)kk * Cout * Cin;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -169,8 +169,9 @@ pack_weight_split_kernel(const float* __restrict__ w, int Cout, int Cin, int kk,
     const float v = w[((int64_t)co * Cin + ci) * kk + tap];
     __nv_bfloat16 h, l;
     split_bf16(v, h, l);
-    hi[i] = h;
-    lo[i] = l;
+    const int64_t o = ((int64_t)tap * Cout_pad + co) * Cin + ci;
+    hi[o] = h;
+    lo[o] = l;
   }
 }
 
@@ -302,13 +303,19 @@ int bbdm_linear_f32(const float* x, const float* w, const float* bias, float* ou
   return BBDM_OK;
 }
 
-int bbdm_pack_weight_split(const float* w, int Cout, int Cin, int k, void* w_hi, void* w_lo, void* stream) {
-  BBDM_REQUIRE(w && w_hi && w_lo && Cout > 0 && Cin > 0 && (k == 1 || k == 3), "pack_weight_split: bad args");
+int bbdm_pack_weight_split_padded(const float* w, int Cout, int Cin, int k, int Cout_pad, void* w_hi, void* w_lo,
+                                  void* stream) {
+  BBDM_REQUIRE(w && w_hi && w_lo && Cout > 0 && Cin > 0 && (k == 1 || k == 3) && Cout_pad >= Cout,
+               "pack_weight_split: bad args");
   const int64_t n = (int64_t)k * k * Cout * Cin;
   pack_weight_split_kernel<<<grid_for(n, 256, num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(
-      w, Cout, Cin, k * k, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo);
+      w, Cout, Cin, k * k, Cout_pad, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo);
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
+}
+
+int bbdm_pack_weight_split(const float* w, int Cout, int Cin, int k, void* w_hi, void* w_lo, void* stream) {
+  return bbdm_pack_weight_split_padded(w, Cout, Cin, k, Cout, w_hi, w_lo, stream);
 }
 
 int bbdm_pack_weight_f32(const float* w, int Cout, int Cin, int k, float* out, void* stream) {

@@ -35,8 +35,28 @@ gn_partial_kernel(const float* __restrict__ s1, int c1, const float* __restrict_
       const float* base;
       int cs, cc;
       if (c < c1) { base = s1; cs = c1; cc = c; } else { base = s2; cs = c2; cc = c - c1; }
-      for (int64_t p = p0 + row; p < p1; p += R) {
-        const float* ptr = base + ((int64_t)b * HW + p) * cs + cc;
+      // 4 independent loads in flight per thread, accumulated in a fixed order (deterministic)
+      const float* ptr0 = base + (int64_t)b * HW * cs + cc;
+      int64_t p = p0 + row;
+      for (; p + 3 * (int64_t)R < p1; p += 4 * (int64_t)R) {
+        float x[4][VEC];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float* ptr = ptr0 + (p + (int64_t)u * R) * cs;
+          if (VEC == 4) {
+            const float4 t = ld_f4(ptr);
+            x[u][0] = t.x; x[u][1 % VEC] = t.y; x[u][2 % VEC] = t.z; x[u][3 % VEC] = t.w;
+          } else {
+            x[u][0] = *ptr;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) { a[v] += (double)x[u][v]; q[v] += (double)x[u][v] * (double)x[u][v]; }
+      }
+      for (; p < p1; p += R) {
+        const float* ptr = ptr0 + p * cs;
         float x[VEC];
         if (VEC == 4) {
           const float4 t = ld_f4(ptr);
@@ -132,69 +152,66 @@ __device__ __forceinline__ void store_vec(float* f32, __nv_bfloat16* hi, __nv_bf
   }
 }
 
+// One CTA per output image row (b, h).  The per-channel affine of this sample
+//   y = x * sc + sh,  sc = rstd*gamma*(1+film_scale),  sh = (beta - mean*rstd*gamma)*(1+film_scale) + film_shift
+// is folded once per CTA into shared memory; the element loop is then 1 FMA + SiLU per value,
+// free of integer division (thread -> (pixel lane, channel chunk) is fixed).
 template <int VEC>
 __global__ void __launch_bounds__(256)
-prep_kernel(const PrepParams p) {
-  const int CV = p.C / VEC;
-  const int64_t total = (int64_t)p.B * p.H * p.W * CV;
+prep_kernel(const PrepParams p, int TPP, int NCH, int R) {
+  extern __shared__ float aff[];            // [C] scale, [C] shift
+  float* sc = aff;
+  float* sh = aff + p.C;
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const bool want_act = p.mean != nullptr;
   const bool want_raw = p.raw_f32 || p.raw_hi;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % CV) * VEC;
-    int64_t pix = i / CV;
-    const int w = (int)(pix % p.W);
-    pix /= p.W;
-    const int h = (int)(pix % p.H);
-    const int b = (int)(pix / p.H);
-
-    // per-channel affine: y = x * sc + sh  (GN affine with FiLM folded on top)
-    float sc[VEC], sh[VEC], f1[VEC], f0[VEC];
-    if (want_act) {
+  if (want_act) {
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+      const int g = c / p.cpg;
+      const float s0 = p.rstd[b * p.groups + g] * p.gamma[c];
+      const float h0 = p.beta[c] - p.mean[b * p.groups + g] * s0;
+      float f1 = 1.0f, f0 = 0.0f;
+      if (p.fscale) { f1 = 1.0f + p.fscale[(int64_t)b * p.fstride + c]; f0 = p.fshift[(int64_t)b * p.fstride + c]; }
+      sc[c] = s0 * f1;
+      sh[c] = fmaf(h0, f1, f0);
+    }
+    __syncthreads();
+  }
+  const int lane_c = threadIdx.x % TPP, pl = threadIdx.x / TPP;
+  if (pl >= R) return;
+  int n_src = 1, hs0 = h;
+  if (p.resample == BBDM_RESAMPLE_UP2) hs0 = h >> 1;
+  else if (p.resample == BBDM_RESAMPLE_DOWN2) { hs0 = h * 2; n_src = 4; }
+  for (int w = pl; w < p.W; w += R) {
+    int ws0 = w;
+    if (p.resample == BBDM_RESAMPLE_UP2) ws0 = w >> 1;
+    else if (p.resample == BBDM_RESAMPLE_DOWN2) ws0 = w * 2;
+    const int64_t obase = (((int64_t)b * p.H + h) * p.W + w) * p.C;
+    for (int j = 0; j < NCH; ++j) {
+      const int c = (lane_c + j * TPP) * VEC;
+      float a[VEC], s[VEC], act[VEC], raw[VEC];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const int g = (c + v) / p.cpg;
-        const float mu = p.mean[b * p.groups + g], rs = p.rstd[b * p.groups + g];
-        const float ga = p.gamma[c + v], be = p.beta[c + v];
-        sc[v] = rs * ga;
-        sh[v] = be - mu * sc[v];
-        if (p.fscale) {
-          f1[v] = 1.0f + p.fscale[(int64_t)b * p.fstride + c + v];
-          f0[v] = p.fshift[(int64_t)b * p.fstride + c + v];
-        } else {
-          f1[v] = 1.0f;
-          f0[v] = 0.0f;
+      for (int v = 0; v < VEC; ++v) { act[v] = raw[v] = 0.0f; a[v] = want_act ? sc[c + v] : 0.f; s[v] = want_act ? sh[c + v] : 0.f; }
+      for (int k = 0; k < n_src; ++k) {
+        float x[VEC];
+        load_vec<VEC>(p, b, hs0 + (k >> 1), ws0 + (k & 1), c, x);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          raw[v] += x[v];
+          if (want_act) {
+            float y = fmaf(x[v], a[v], s[v]);
+            if (p.silu) y = __fdividef(y, 1.0f + __expf(-y));
+            act[v] += y;
+          }
         }
       }
-    }
-    float act[VEC], raw[VEC];
+      if (n_src == 4) {
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) act[v] = raw[v] = 0.0f;
-
-    int n_src = 1, hs0 = h, ws0 = w;
-    if (p.resample == BBDM_RESAMPLE_UP2) { hs0 = h >> 1; ws0 = w >> 1; }
-    else if (p.resample == BBDM_RESAMPLE_DOWN2) { hs0 = h * 2; ws0 = w * 2; n_src = 4; }
-    for (int k = 0; k < n_src; ++k) {
-      float x[VEC];
-      load_vec<VEC>(p, b, hs0 + (k >> 1), ws0 + (k & 1), c, x);
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        raw[v] += x[v];
-        if (want_act) {
-          float y = fmaf(x[v], sc[v], sh[v]);
-          if (p.fscale) y = fmaf(y, f1[v], f0[v]);
-          if (p.silu) y = silu_f(y);
-          act[v] += y;
-        }
+        for (int v = 0; v < VEC; ++v) { act[v] *= 0.25f; raw[v] *= 0.25f; }
       }
+      if (want_act) store_vec<VEC>(p.act_f32, p.act_hi, p.act_lo, obase + c, act);
+      if (want_raw) store_vec<VEC>(p.raw_f32, p.raw_hi, p.raw_lo, obase + c, raw);
     }
-    if (n_src == 4) {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) { act[v] *= 0.25f; raw[v] *= 0.25f; }
-    }
-    const int64_t off = (((int64_t)b * p.H + h) * p.W + w) * p.C + c;
-    if (want_act) store_vec<VEC>(p.act_f32, p.act_hi, p.act_lo, off, act);
-    if (want_raw) store_vec<VEC>(p.raw_f32, p.raw_hi, p.raw_lo, off, raw);
   }
 }
 
@@ -219,9 +236,9 @@ int bbdm_gn_stats(const float* src1, int c1, const float* src2, int c2, int B, i
   int R = 256 / L;
   if (R > 8) R = 8;
   if ((int64_t)R > HW) R = (int)HW;
-  int S = (2 * num_sms() + B - 1) / B;
+  int S = (8 * num_sms() + B - 1) / B;
   if (S > BBDM_GN_MAX_SLICES) S = BBDM_GN_MAX_SLICES;
-  if ((int64_t)S * R * 4 > HW) S = (int)(HW / ((int64_t)R * 4));
+  if ((int64_t)S * R * 16 > HW) S = (int)(HW / ((int64_t)R * 16));
   if (S < 1) S = 1;
   const size_t smem = (size_t)C * 2 * sizeof(double);
   BBDM_REQUIRE(smem <= 160 * 1024, "gn_stats: C=%d too large", C);
@@ -273,12 +290,19 @@ int bbdm_prep_operand(const BbdmPrepArgs* a, void* stream) {
                "prep_operand: hi/lo planes must come in pairs");
   BBDM_REQUIRE(p.mean || p.raw_f32 || p.raw_hi, "prep_operand: nothing to do");
   const bool vec4 = (p.c1 % 4 == 0) && (p.c2 % 4 == 0);
-  const int64_t total = (int64_t)p.B * p.H * p.W * (p.C / (vec4 ? 4 : 1));
-  int64_t g = (total + 255) / 256;
-  const int64_t gmax = (int64_t)num_sms() * 16;
-  if (g > gmax) g = gmax;
-  if (vec4) prep_kernel<4><<<(int)g, 256, 0, (cudaStream_t)stream>>>(p);
-  else prep_kernel<1><<<(int)g, 256, 0, (cudaStream_t)stream>>>(p);
+  const int CV = p.C / (vec4 ? 4 : 1);
+  // threads per pixel: the largest divisor of CV that is <= 128; each thread owns NCH chunks
+  int TPP = 1;
+  for (int d = 1; d <= 128 && d <= CV; ++d) if (CV % d == 0) TPP = d;
+  const int NCH = CV / TPP;
+  int R = 256 / TPP;
+  if (R > p.W) R = p.W;
+  const int64_t rows = (int64_t)p.B * p.H;
+  BBDM_REQUIRE(rows < (1ll << 31), "prep_operand: too many rows");
+  const size_t smem = (size_t)p.C * 2 * sizeof(float);
+  BBDM_REQUIRE(smem <= 48 * 1024, "prep_operand: C=%d too large", p.C);
+  if (vec4) prep_kernel<4><<<(unsigned)rows, 256, smem, (cudaStream_t)stream>>>(p, TPP, NCH, R);
+  else prep_kernel<1><<<(unsigned)rows, 256, smem, (cudaStream_t)stream>>>(p, TPP, NCH, R);
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
 }

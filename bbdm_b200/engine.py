@@ -106,6 +106,19 @@ class UNetEngine:
                 lo = buf(name, "lo", (k * k, cout, cin), torch.bfloat16)
                 be.pack_weight_split(wt, hi, lo)
                 ent["hi"], ent["lo"] = hi, lo
+            elif name == "out.2" and cin % 64 == 0 and cout < 64 and k == 3:
+                # UNet head (Cout = 3..16): zero-padded to one 64-wide N tile of the tensor-core conv
+                made = not (isinstance(old.get(name), dict) and "hi_pad" in old[name])
+                hi = buf(name, "hi_pad", (k * k, 64, cin), torch.bfloat16)
+                lo = buf(name, "lo_pad", (k * k, 64, cin), torch.bfloat16)
+                bp = buf(name, "bias_pad", (64,), torch.float32)
+                if made:
+                    hi.zero_(); lo.zero_()
+                bp.zero_()
+                if conv.bias is not None:
+                    bp[:cout].copy_(conv.bias.detach())
+                be.pack_weight_split(wt, hi, lo)
+                ent["hi_pad"], ent["lo_pad"], ent["bias_pad"] = hi, lo, bp
             f32 = buf(name, "f32", (k * k, cin, cout), torch.float32)
             be.pack_weight_f32(wt, f32)
             ent["f32"] = f32
@@ -287,18 +300,20 @@ class UNetEngine:
                 beta=m.norm.bias.detach(), silu=False, resample=cabi.RESAMPLE_NONE,
                 act_f32=a_f32, act_hi=a_hi, act_lo=a_lo)
         pool.put(mean, rstd)
-        qkv, _, _ = self._conv(pool, eq, a_f32=a_f32, a_hi=a_hi, a_lo=a_lo, shape=(B, H, W))
+        # qkv 1x1: on the tensor-core path its epilogue writes the split planes the attention core reads
+        qkv, q_hi, q_lo = self._conv(pool, eq, a_f32=a_f32, a_hi=a_hi, a_lo=a_lo, shape=(B, H, W),
+                                     out_split=umma, want_f32=not umma)
         pool.put(a_f32, a_hi, a_lo)
         o_f32 = o_hi = o_lo = None
+        order = 1 if m.new_order else 0
         if umma:
             o_hi, o_lo = pool.get(x.shape, torch.bfloat16), pool.get(x.shape, torch.bfloat16)
+            be.attention_split(q_hi.view(B, T, 3 * Cc), q_lo.view(B, T, 3 * Cc), heads, order,
+                               None, o_hi.view(B, T, Cc), o_lo.view(B, T, Cc))
         else:
             o_f32 = pool.get(x.shape)
-        be.attention(qkv.view(B, T, 3 * Cc), heads, 1 if m.new_order else 0,
-                     None if o_f32 is None else o_f32.view(B, T, Cc),
-                     None if o_hi is None else o_hi.view(B, T, Cc),
-                     None if o_lo is None else o_lo.view(B, T, Cc))
-        pool.put(qkv)
+            be.attention(qkv.view(B, T, 3 * Cc), heads, order, o_f32.view(B, T, Cc), None, None)
+        pool.put(qkv, q_hi, q_lo)
         out, _, _ = self._conv(pool, ep, a_f32=o_f32, a_hi=o_hi, a_lo=o_lo, shape=(B, H, W),
                                residual=x, res_mode=cabi.RES_SAME)
         pool.put(o_f32, o_hi, o_lo)
@@ -391,14 +406,26 @@ class UNetEngine:
         # ---- head: GN -> SiLU -> conv3x3 -> NCHW ----------------------------------------------------
         mean, rstd = self._stats(pool, h, None)
         gn = u.out[0]
+        if out is None:
+            out = torch.empty((B, u.out_channels, H, W), dtype=torch.float32, device=dev)
+        eh = w["out.2"]
+        if "hi_pad" in eh and W >= 4:
+            # tensor-core head: N tile padded to 64 couts, epilogue stores the real ones as NCHW
+            a_hi, a_lo = pool.get(h.shape, torch.bfloat16), pool.get(h.shape, torch.bfloat16)
+            be.prep(h, None, groups=GN_GROUPS, mean=mean, rstd=rstd, gamma=gn.weight.detach(), beta=gn.bias.detach(),
+                    silu=True, resample=cabi.RESAMPLE_NONE, act_hi=a_hi, act_lo=a_lo)
+            pool.put(mean, rstd, h)
+            be.conv_umma(B=B, H=H, W=W, Cin=eh["cin"], Cout=64, taps=9, a_hi=a_hi, a_lo=a_lo, w_hi=eh["hi_pad"],
+                         w_lo=eh["lo_pad"], bias=eh["bias_pad"], out=out, passes=self.passes,
+                         out_nchw_channels=u.out_channels)
+            pool.put(a_hi, a_lo, emb, film)
+            return out
         act = pool.get(h.shape)
         be.prep(h, None, groups=GN_GROUPS, mean=mean, rstd=rstd, gamma=gn.weight.detach(), beta=gn.bias.detach(),
                 silu=True, resample=cabi.RESAMPLE_NONE, act_f32=act)
         pool.put(mean, rstd, h)
-        y, _, _ = self._conv(pool, w["out.2"], a_f32=act, shape=(B, H, W))
+        y, _, _ = self._conv(pool, eh, a_f32=act, shape=(B, H, W))
         pool.put(act)
-        if out is None:
-            out = torch.empty((B, u.out_channels, H, W), dtype=torch.float32, device=dev)
         be.nhwc_to_nchw(y, out)
         pool.put(y, emb, film)
         return out

@@ -157,6 +157,11 @@ int bbdm_prep_operand(const BbdmPrepArgs* a, void* stream);
  *   f32:    fp32 [k*k][Cin][Cout]         (direct kernel) */
 int bbdm_pack_weight_split(const float* w, int Cout, int Cin, int k, void* w_hi, void* w_lo,
                            void* stream);
+/* Same, into planes of Cout_pad >= Cout rows per tap (rows >= Cout must be pre-zeroed by the
+ * caller): lets a conv with few output channels (the UNet head, Cout = 3..16) use the
+ * tensor-core kernel with an N tile of 64. */
+int bbdm_pack_weight_split_padded(const float* w, int Cout, int Cin, int k, int Cout_pad,
+                                  void* w_hi, void* w_lo, void* stream);
 int bbdm_pack_weight_f32(const float* w, int Cout, int Cin, int k, float* out, void* stream);
 
 enum { BBDM_RES_NONE = 0, BBDM_RES_SAME = 1, BBDM_RES_UP2 = 2, BBDM_RES_DOWN2 = 3 };
@@ -186,6 +191,9 @@ typedef struct {
   float* out;                 /* fp32 [B,H,W,Cout] or NULL                   */
   void* out_hi; void* out_lo; /* optional split-bf16 copy of the result      */
   int passes;
+  int out_nchw_channels;      /* > 0: `out` is NCHW [B, out_nchw_channels, H, W] and only the first
+                                 out_nchw_channels (<= Cout) couts are stored (UNet head, replaces
+                                 the final layout change); 0: NHWC [B,H,W,Cout]             */
 } BbdmConvArgs;
 int bbdm_conv_umma(const BbdmConvArgs* a, void* stream);
 
@@ -209,6 +217,12 @@ int bbdm_conv_direct(const float* src, const float* w_packed, const float* bias,
  * Split-bf16 tensor-core products with fp32 accumulation.  head_dim in {16,32,64}. */
 int bbdm_attention(const float* qkv, int B, int T, int C, int heads, int order,
                    float* out_f32, void* out_hi, void* out_lo, void* stream);
+
+/* Same attention core on PRE-SPLIT bf16 planes qkv_hi/qkv_lo [B,T,3C] (written by the qkv
+ * conv's epilogue, BbdmConvArgs.out_hi/out_lo): no conversion or re-splitting of K/V per query
+ * tile; cp.async double-buffered KV tiles, ldmatrix fragments, 128 queries per CTA. */
+int bbdm_attention_split(const void* qkv_hi, const void* qkv_lo, int B, int T, int C, int heads,
+                         int order, float* out_f32, void* out_hi, void* out_lo, void* stream);
 
 #ifdef __cplusplus
 }

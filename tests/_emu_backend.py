@@ -32,6 +32,7 @@ class EmuBackend:
         h, l = O.bf16_split(x.float())
         hi.copy_(h.to(torch.bfloat16))
         lo.copy_(l.to(torch.bfloat16))
+        assert not torch.isnan(hi.float()).any()
 
     # -- bridge ----------------------------------------------------------------------------------
     def q_sample(self, x0, y, noise, t, m_t, var_t, objective, xt_out, obj_out):
@@ -112,7 +113,7 @@ class EmuBackend:
     def pack_weight_split(self, w, hi, lo):
         self.calls.append("pack_weight_split")
         cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
-        self._write_split(w.permute(2, 3, 0, 1).reshape(k * k, cout, cin), hi, lo)
+        self._write_split(w.permute(2, 3, 0, 1).reshape(k * k, cout, cin), hi[:, :cout], lo[:, :cout])
 
     def pack_weight_f32(self, w, out):
         self.calls.append("pack_weight_f32")
@@ -127,7 +128,7 @@ class EmuBackend:
 
     def conv_umma(self, *, B, H, W, Cin, Cout, taps, a_hi, a_lo, w_hi, w_lo, bias=None, Cin2=0,
                   a2_hi=None, a2_lo=None, w2_hi=None, w2_lo=None, bias2=None, residual=None,
-                  res_mode=0, out=None, out_hi=None, out_lo=None, passes=3):
+                  res_mode=0, out=None, out_hi=None, out_lo=None, passes=3, out_nchw_channels=0):
         self.calls.append("conv_umma")
         assert Cin % 64 == 0 and Cout % 64 == 0 and Cin2 % 64 == 0 and W >= 4
         a = self._planes(a_hi, a_lo).reshape(B, H, W, Cin)
@@ -142,7 +143,9 @@ class EmuBackend:
             o = o + O.op_resample(residual.reshape(B, H // 2, W // 2, Cout), 1)
         elif res_mode == 3:
             o = o + O.op_resample(residual.reshape(B, H * 2, W * 2, Cout), 2)
-        if out is not None:
+        if out_nchw_channels:
+            out.copy_(o[..., :out_nchw_channels].permute(0, 3, 1, 2))
+        elif out is not None:
             out.copy_(o.reshape(out.shape))
         if out_hi is not None:
             self._write_split(o.reshape(out_hi.shape), out_hi, out_lo)
@@ -165,6 +168,10 @@ class EmuBackend:
             out_f32.copy_(o)
         if out_hi is not None:
             self._write_split(o, out_hi, out_lo)
+
+    def attention_split(self, qkv_hi, qkv_lo, heads, order, out_f32=None, out_hi=None, out_lo=None):
+        self.calls.append("attention_split")
+        self.attention(self._planes(qkv_hi, qkv_lo), heads, order, out_f32, out_hi, out_lo)
 
     def check_fault(self):
         pass
