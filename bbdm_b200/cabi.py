@@ -26,7 +26,7 @@ SYMBOLS = [
     "bbdm_bridge_q_sample", "bbdm_bridge_p_sample", "bbdm_bridge_p_sample_dev", "bbdm_nchw_to_nhwc_cat", "bbdm_nhwc_to_nchw",
     "bbdm_gather_rows", "bbdm_linear_f32", "bbdm_gn_stats", "bbdm_prep_operand",
     "bbdm_pack_weight_split", "bbdm_pack_weight_split_padded", "bbdm_pack_weight_f32", "bbdm_conv_umma", "bbdm_conv_direct",
-    "bbdm_attention", "bbdm_attention_split",
+    "bbdm_attention", "bbdm_attention_split", "bbdm_conv_umma_geometry", "bbdm_gn_finalize_partials",
 ]
 
 
@@ -56,7 +56,7 @@ class ConvArgs(C.Structure):
                 ("bias2", C.c_void_p),
                 ("residual", C.c_void_p), ("res_mode", C.c_int),
                 ("out", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
-                ("passes", C.c_int), ("out_nchw_channels", C.c_int)]
+                ("passes", C.c_int), ("out_nchw_channels", C.c_int), ("stats_partial", C.c_void_p)]
 
 
 class BbdmError(RuntimeError):
@@ -96,6 +96,8 @@ def load():
     lib.bbdm_conv_umma.argtypes = [C.POINTER(ConvArgs), vp]
     lib.bbdm_conv_direct.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
     lib.bbdm_attention.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp]
+    lib.bbdm_conv_umma_geometry.argtypes = [i, i, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]
+    lib.bbdm_gn_finalize_partials.argtypes = [vp, i, i, vp, i, i, i, i, i, f, vp, vp, vp]
     lib.bbdm_attention_split.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp]
     for s in SYMBOLS:
         fn = getattr(lib, s)
@@ -232,11 +234,26 @@ class CudaBackend:
 
     def conv_umma(self, *, B, H, W, Cin, Cout, taps, a_hi, a_lo, w_hi, w_lo, bias=None, Cin2=0,
                   a2_hi=None, a2_lo=None, w2_hi=None, w2_lo=None, bias2=None, residual=None,
-                  res_mode=RES_NONE, out=None, out_hi=None, out_lo=None, passes=3, out_nchw_channels=0):
+                  res_mode=RES_NONE, out=None, out_hi=None, out_lo=None, passes=3, out_nchw_channels=0,
+                  stats_partial=None):
         a = ConvArgs(B, H, W, Cin, Cout, taps, ptr(a_hi), ptr(a_lo), ptr(w_hi), ptr(w_lo), ptr(bias),
                      Cin2, ptr(a2_hi), ptr(a2_lo), ptr(w2_hi), ptr(w2_lo), ptr(bias2),
-                     ptr(residual), res_mode, ptr(out), ptr(out_hi), ptr(out_lo), passes, out_nchw_channels)
+                     ptr(residual), res_mode, ptr(out), ptr(out_hi), ptr(out_lo), passes, out_nchw_channels,
+                     ptr(stats_partial))
         check(self.lib.bbdm_conv_umma(C.byref(a), stream()))
+        LAUNCHES["n"] += 1
+
+    def conv_geometry(self, H, W):
+        """(TW, TH, TB, rows_per_image) of the tensor-core conv for an HxW output."""
+        v = [C.c_int(0) for _ in range(4)]
+        check(self.lib.bbdm_conv_umma_geometry(H, W, *[C.byref(z) for z in v]))
+        return tuple(z.value for z in v)
+
+    def gn_finalize_partials(self, part1, rows1, part2, rows2, B, hw, groups, eps, mean, rstd):
+        c1 = part1.shape[1]
+        c2 = 0 if part2 is None else part2.shape[1]
+        check(self.lib.bbdm_gn_finalize_partials(ptr(_req(part1)), c1, rows1, ptr(part2), c2, rows2, B, hw, groups,
+                                                 eps, ptr(_req(mean)), ptr(_req(rstd)), stream()))
         LAUNCHES["n"] += 1
 
     def conv_direct(self, src, w_packed, bias, residual, out, Cout, k, stride=1):

@@ -120,6 +120,21 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   return d;
 }
 
+// Column sums over the 32 lanes (rows) of a warp for 32 per-lane values: reduce-scatter
+// butterfly, 31 shuffles; afterwards lane l holds the total of column l in v[0].
+__device__ __forceinline__ void warp_colsum32(float* v, int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const bool up = (lane & off) != 0;
+      const float keep = up ? v[i + off] : v[i];
+      const float send = up ? v[i] : v[i + off];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
 struct ConvParams {
   int B, H, W, Cout;
   int TW, TH, TB, tiles_w, tiles_h, tiles_b, n_tiles;
@@ -133,6 +148,7 @@ struct ConvParams {
   const float* residual; int res_mode;
   float* out; __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
   int out_nchw_c;    // > 0: out is NCHW with this many channels (UNet head)
+  float* stats;      // fused GroupNorm partial sums (see BbdmConvArgs.stats_partial) or nullptr
   unsigned long long* fault;
 };
 
@@ -326,11 +342,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       // ---- tile epilogue: bias / fused-skip bias / residual / store ------------------------------
-      if (valid) {
+      {
 #pragma unroll
         for (int ch = 0; ch < COLS / 32; ++ch) {
           const int nc = n0 + ch * 32;
           float* r = &racc[ch * 32];
+          if (valid) {
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -391,6 +408,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               *reinterpret_cast<uint2*>(p.out_hi + pix * p.Cout + nc + j) = h;
               *reinterpret_cast<uint2*>(p.out_lo + pix * p.Cout + nc + j) = l;
             }
+          }
+          }   // valid
+          if (p.stats) {
+            // fused GroupNorm statistics of the tensor just written: per-channel (sum, sum sq) over
+            // this warp's 32 pixel rows (tile lies inside one image: TB == 1)
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { if (!valid) r[j] = 0.f; sq[j] = r[j] * r[j]; }
+            warp_colsum32(r, lane);
+            warp_colsum32(sq, lane);
+            const int64_t prow = ((int64_t)tb * p.tiles_w * p.tiles_h + th * p.tiles_w + tw) * 4 + q;
+            *reinterpret_cast<float2*>(p.stats + (prow * p.Cout + nc + lane) * 2) = make_float2(r[0], sq[0]);
           }
         }
       }
@@ -478,6 +507,24 @@ static int launch_conv(const CUtensorMap* maps, const ConvParams& p, int grid, c
 
 using namespace bbdm;
 
+static void tile_geometry(int H, int W, int* TW, int* TH, int* TB) {
+  *TW = pow2_floor(W) < 16 ? pow2_floor(W) : 16;
+  const int th = pow2_ceil(H);
+  *TH = th < UM_BM / *TW ? th : UM_BM / *TW;
+  *TB = UM_BM / (*TW * *TH);
+}
+
+extern "C" int bbdm_conv_umma_geometry(int H, int W, int* TW, int* TH, int* TB, int* rows_per_image) {
+  BBDM_REQUIRE(H > 0 && W >= 4, "conv_umma_geometry: need H > 0, W >= 4");
+  int tw, th, tb;
+  tile_geometry(H, W, &tw, &th, &tb);
+  if (TW) *TW = tw;
+  if (TH) *TH = th;
+  if (TB) *TB = tb;
+  if (rows_per_image) *rows_per_image = tb == 1 ? 4 * ((W + tw - 1) / tw) * ((H + th - 1) / th) : 0;
+  return BBDM_OK;
+}
+
 extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   BBDM_REQUIRE(a != nullptr, "conv_umma: null args");
   BBDM_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0, "conv_umma: bad spatial shape");
@@ -496,10 +543,7 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
 
   ConvParams p;
   p.B = a->B; p.H = a->H; p.W = a->W; p.Cout = a->Cout;
-  p.TW = pow2_floor(a->W) < 16 ? pow2_floor(a->W) : 16;
-  int th = pow2_ceil(a->H);
-  p.TH = th < UM_BM / p.TW ? th : UM_BM / p.TW;
-  p.TB = UM_BM / (p.TW * p.TH);
+  tile_geometry(a->H, a->W, &p.TW, &p.TH, &p.TB);
   p.tiles_w = (a->W + p.TW - 1) / p.TW;
   p.tiles_h = (a->H + p.TH - 1) / p.TH;
   p.tiles_b = (a->B + p.TB - 1) / p.TB;
@@ -514,11 +558,14 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   p.residual = a->residual; p.res_mode = a->res_mode;
   p.out = a->out; p.out_hi = (__nv_bfloat16*)a->out_hi; p.out_lo = (__nv_bfloat16*)a->out_lo;
   p.out_nchw_c = a->out_nchw_channels;
+  p.stats = a->stats_partial;
   BBDM_REQUIRE(p.out_nchw_c >= 0 && p.out_nchw_c <= a->Cout && (p.out_nchw_c == 0 || (a->out && !a->out_hi)),
                "conv_umma: bad out_nchw_channels");
   p.fault = device_fault_ptr();
   BBDM_REQUIRE(p.fault != nullptr, "conv_umma: device fault word unavailable");
 
+  BBDM_REQUIRE(p.stats == nullptr || (p.TB == 1 && p.out_nchw_c == 0),
+               "conv_umma: stats_partial needs a tile inside one image (H*W >= 128) and NHWC output");
   const int BN = (a->Cout % 256 == 0) ? 256 : (a->Cout % 128 == 0 ? 128 : 64);
   CUtensorMap maps[8];
   int rc;

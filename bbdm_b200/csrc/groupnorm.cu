@@ -101,6 +101,44 @@ __global__ void gn_finalize_kernel(const double* __restrict__ ws, int S, int gro
   rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// Statistics from the partial sums fused into the conv epilogues: one CTA per (b, group);
+// thread i owns (row, channel-in-group) pairs i, i+256, ... in a fixed order, then a fixed
+// shared-memory tree in fp64 => deterministic.
+__global__ void __launch_bounds__(256)
+gn_from_partials_kernel(const float* __restrict__ p1, int c1, int rows1, const float* __restrict__ p2, int c2,
+                        int rows2, int groups, double count, float eps, float* __restrict__ mean,
+                        float* __restrict__ rstd) {
+  __shared__ double sa[256], sq[256];
+  const int b = blockIdx.x / groups, g = blockIdx.x % groups;
+  const int cpg = (c1 + c2) / groups;
+  double a = 0.0, q = 0.0;
+  for (int cc = 0; cc < cpg; ++cc) {
+    const int c = g * cpg + cc;
+    const float* base;
+    int cs, ci, rows;
+    if (c < c1) { base = p1; cs = c1; ci = c; rows = rows1; } else { base = p2; cs = c2; ci = c - c1; rows = rows2; }
+    for (int r = threadIdx.x; r < rows; r += 256) {
+      const float2 v = *reinterpret_cast<const float2*>(base + (((int64_t)b * rows + r) * cs + ci) * 2);
+      a += (double)v.x;
+      q += (double)v.y;
+    }
+  }
+  sa[threadIdx.x] = a;
+  sq[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sq[threadIdx.x] += sq[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double m = sa[0] / count;
+    double var = sq[0] / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[blockIdx.x] = (float)m;
+    rstd[blockIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Operand preparation.
 // ------------------------------------------------------------------------------------------
@@ -182,35 +220,66 @@ prep_kernel(const PrepParams p, int TPP, int NCH, int R) {
   int n_src = 1, hs0 = h;
   if (p.resample == BBDM_RESAMPLE_UP2) hs0 = h >> 1;
   else if (p.resample == BBDM_RESAMPLE_DOWN2) { hs0 = h * 2; n_src = 4; }
-  for (int w = pl; w < p.W; w += R) {
-    int ws0 = w;
-    if (p.resample == BBDM_RESAMPLE_UP2) ws0 = w >> 1;
-    else if (p.resample == BBDM_RESAMPLE_DOWN2) ws0 = w * 2;
-    const int64_t obase = (((int64_t)b * p.H + h) * p.W + w) * p.C;
+  // U pixels per iteration: U independent 16-byte loads in flight per thread before any math
+  constexpr int U = 4;
+  for (int w0 = pl; w0 < p.W; w0 += U * R) {
     for (int j = 0; j < NCH; ++j) {
       const int c = (lane_c + j * TPP) * VEC;
-      float a[VEC], s[VEC], act[VEC], raw[VEC];
+      float a[VEC], s[VEC];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) { act[v] = raw[v] = 0.0f; a[v] = want_act ? sc[c + v] : 0.f; s[v] = want_act ? sh[c + v] : 0.f; }
-      for (int k = 0; k < n_src; ++k) {
-        float x[VEC];
-        load_vec<VEC>(p, b, hs0 + (k >> 1), ws0 + (k & 1), c, x);
+      for (int v = 0; v < VEC; ++v) { a[v] = want_act ? sc[c + v] : 0.f; s[v] = want_act ? sh[c + v] : 0.f; }
+      if (n_src == 1) {
+        float x[U][VEC];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          raw[v] += x[v];
+        for (int u = 0; u < U; ++u) {
+          const int w = w0 + u * R;
+          if (w < p.W) load_vec<VEC>(p, b, hs0, (p.resample == BBDM_RESAMPLE_UP2) ? (w >> 1) : w, c, x[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int w = w0 + u * R;
+          if (w >= p.W) continue;
+          float act[VEC];
           if (want_act) {
-            float y = fmaf(x[v], a[v], s[v]);
-            if (p.silu) y = __fdividef(y, 1.0f + __expf(-y));
-            act[v] += y;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              float y = fmaf(x[u][v], a[v], s[v]);
+              if (p.silu) y = __fdividef(y, 1.0f + __expf(-y));
+              act[v] = y;
+            }
           }
+          const int64_t off = (((int64_t)b * p.H + h) * p.W + w) * p.C + c;
+          if (want_act) store_vec<VEC>(p.act_f32, p.act_hi, p.act_lo, off, act);
+          if (want_raw) store_vec<VEC>(p.raw_f32, p.raw_hi, p.raw_lo, off, x[u]);
+        }
+      } else {
+        // 2x2 average pooling of the activated (and of the raw) tensor
+        for (int u = 0; u < U; ++u) {
+          const int w = w0 + u * R;
+          if (w >= p.W) continue;
+          float x[4][VEC], act[VEC], raw[VEC];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) load_vec<VEC>(p, b, hs0 + (k >> 1), w * 2 + (k & 1), c, x[k]);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            act[v] = raw[v] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              raw[v] += x[k][v];
+              if (want_act) {
+                float y = fmaf(x[k][v], a[v], s[v]);
+                if (p.silu) y = __fdividef(y, 1.0f + __expf(-y));
+                act[v] += y;
+              }
+            }
+            act[v] *= 0.25f;
+            raw[v] *= 0.25f;
+          }
+          const int64_t off = (((int64_t)b * p.H + h) * p.W + w) * p.C + c;
+          if (want_act) store_vec<VEC>(p.act_f32, p.act_hi, p.act_lo, off, act);
+          if (want_raw) store_vec<VEC>(p.raw_f32, p.raw_hi, p.raw_lo, off, raw);
         }
       }
-      if (n_src == 4) {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) { act[v] *= 0.25f; raw[v] *= 0.25f; }
-      }
-      if (want_act) store_vec<VEC>(p.act_f32, p.act_hi, p.act_lo, obase + c, act);
-      if (want_raw) store_vec<VEC>(p.raw_f32, p.raw_hi, p.raw_lo, obase + c, raw);
     }
   }
 }
@@ -256,6 +325,17 @@ int bbdm_gn_stats(const float* src1, int c1, const float* src2, int c2, int B, i
   BBDM_LAUNCH_CHECK();
   const int n = B * groups;
   gn_finalize_kernel<<<(n + 127) / 128, 128, 0, s>>>(workspace, S, groups, (double)HW * (C / groups), eps, mean, rstd, n);
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
+int bbdm_gn_finalize_partials(const float* part1, int c1, int rows1, const float* part2, int c2, int rows2,
+                              int B, int hw, int groups, float eps, float* mean, float* rstd, void* stream) {
+  BBDM_REQUIRE(part1 && mean && rstd && c1 > 0 && rows1 > 0 && B > 0 && hw > 0 && groups > 0, "gn_finalize_partials: bad args");
+  if (!part2) { c2 = 0; rows2 = 0; }
+  BBDM_REQUIRE((c1 + c2) % groups == 0, "gn_finalize_partials: C %% groups != 0");
+  gn_from_partials_kernel<<<B * groups, 256, 0, (cudaStream_t)stream>>>(
+      part1, c1, rows1, part2, c2, rows2, groups, (double)hw * ((c1 + c2) / groups), eps, mean, rstd);
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
 }

@@ -44,6 +44,9 @@ class _Pool:
     def put(self, *ts):
         for t in ts:
             if t is not None:
+                gn = t.__dict__.pop("_gn", None)      # fused GroupNorm partial sums travel with the tensor
+                if gn is not None:
+                    self.put(gn[0])
                 self.free.setdefault((tuple(t.shape), t.dtype), []).append(t)
 
 
@@ -60,6 +63,7 @@ class UNetEngine:
         self._table = None
         self._gn_ws = None
         self.num_timesteps = 1000
+        self._geom_cache = {}
         self.generation = 0          # bumps whenever cache/parameter ADDRESSES change (graphs key on it)
 
     # ------------------------------------------------------------------------------ weights
@@ -166,6 +170,13 @@ class UNetEngine:
     def _stats(self, pool, src1, src2):
         B = src1.shape[0]
         mean, rstd = pool.get((B, GN_GROUPS)), pool.get((B, GN_GROUPS))
+        g1 = getattr(src1, "_gn", None)
+        g2 = None if src2 is None else getattr(src2, "_gn", None)
+        if g1 is not None and (src2 is None or g2 is not None):
+            # both tensors came out of the tensor-core conv: its epilogue already reduced them
+            self.be.gn_finalize_partials(g1[0], g1[1], None if g2 is None else g2[0], 0 if g2 is None else g2[1],
+                                         B, src1.shape[1] * src1.shape[2], GN_GROUPS, GN_EPS, mean, rstd)
+            return mean, rstd
         if self._gn_ws is None or self._gn_ws.numel() < B * GN_GROUPS * cabi.GN_MAX_SLICES * 2 \
                 or self._gn_ws.device != src1.device:
             self._gn_ws = self.be.empty((B * GN_GROUPS * cabi.GN_MAX_SLICES * 2,), torch.float64, src1.device)
@@ -173,7 +184,8 @@ class UNetEngine:
         return mean, rstd
 
     def _conv(self, pool, ent, *, a_f32=None, a_hi=None, a_lo=None, shape, bias=None, residual=None,
-              res_mode=cabi.RES_NONE, second=None, out_split=False, want_f32=True, stride=1, out=None):
+              res_mode=cabi.RES_NONE, second=None, out_split=False, want_f32=True, stride=1, out=None,
+              stats=False):
         """One convolution.  shape = (B,H,W) of the INPUT; returns (out_f32, out_hi, out_lo)."""
         B, H, W = shape
         cout, cin, k = ent["cout"], ent["cin"], ent["k"]
@@ -188,9 +200,16 @@ class UNetEngine:
             if second is not None:
                 e2, r_hi, r_lo = second
                 kw = dict(Cin2=e2["cin"], a2_hi=r_hi, a2_lo=r_lo, w2_hi=e2["hi"], w2_lo=e2["lo"], bias2=e2["bias"])
+            part = None
+            if stats and out is not None:
+                rows = self._geom(H, W)
+                if rows:
+                    part = pool.get((B * rows, cout, 2))
             self.be.conv_umma(B=B, H=H, W=W, Cin=cin, Cout=cout, taps=k * k, a_hi=a_hi, a_lo=a_lo,
                               w_hi=ent["hi"], w_lo=ent["lo"], bias=bias, residual=residual, res_mode=res_mode,
-                              out=out, out_hi=oh, out_lo=ol, passes=self.passes, **kw)
+                              out=out, out_hi=oh, out_lo=ol, passes=self.passes, stats_partial=part, **kw)
+            if part is not None:
+                out._gn = (part, rows)
             return out, oh, ol
         assert second is None and res_mode in (cabi.RES_NONE, cabi.RES_SAME) and not out_split
         Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
@@ -198,6 +217,13 @@ class UNetEngine:
             out = pool.get((B, Ho, Wo, cout))
         self.be.conv_direct(a_f32, ent["f32"], bias, residual, out, cout, k, stride)
         return out, None, None
+
+    def _geom(self, H, W):
+        key = (H, W)
+        r = self._geom_cache.get(key)
+        if r is None:
+            r = self._geom_cache[key] = self.be.conv_geometry(H, W)[3]
+        return r
 
     # ------------------------------------------------------------------------------ blocks
     def _resblock(self, pool, name, m: ResBlock, src1, src2, film):
@@ -236,7 +262,7 @@ class UNetEngine:
                 raw_f32=r_f32, raw_hi=r_hi, raw_lo=r_lo)
         pool.put(mean, rstd)
         if m.use_scale_shift_norm:
-            h1, _, _ = self._conv(pool, e1, a_f32=a_f32, a_hi=a_hi, a_lo=a_lo, shape=(B, H, W))
+            h1, _, _ = self._conv(pool, e1, a_f32=a_f32, a_hi=a_hi, a_lo=a_lo, shape=(B, H, W), stats=True)
         else:
             # conv1 + (bias + emb_out[b]) per sample: per-sample bias rows live in `film`
             h1 = pool.get((B, H, W, cout))
@@ -276,7 +302,7 @@ class UNetEngine:
             res_mode = {cabi.RESAMPLE_NONE: cabi.RES_SAME, cabi.RESAMPLE_UP2: cabi.RES_UP2,
                         cabi.RESAMPLE_DOWN2: cabi.RES_DOWN2}[resample]
         out, _, _ = self._conv(pool, e2, a_f32=b_f32, a_hi=b_hi, a_lo=b_lo, shape=(B, H, W),
-                               residual=residual, res_mode=res_mode, second=second)
+                               residual=residual, res_mode=res_mode, second=second, stats=True)
         pool.put(b_f32, b_hi, b_lo, r_f32, r_hi, r_lo, skip_out)
         return out
 
@@ -315,7 +341,7 @@ class UNetEngine:
             be.attention(qkv.view(B, T, 3 * Cc), heads, order, o_f32.view(B, T, Cc), None, None)
         pool.put(qkv, q_hi, q_lo)
         out, _, _ = self._conv(pool, ep, a_f32=o_f32, a_hi=o_hi, a_lo=o_lo, shape=(B, H, W),
-                               residual=x, res_mode=cabi.RES_SAME)
+                               residual=x, res_mode=cabi.RES_SAME, stats=True)
         pool.put(o_f32, o_hi, o_lo)
         return out
 

@@ -194,8 +194,24 @@ typedef struct {
   int out_nchw_channels;      /* > 0: `out` is NCHW [B, out_nchw_channels, H, W] and only the first
                                  out_nchw_channels (<= Cout) couts are stored (UNet head, replaces
                                  the final layout change); 0: NHWC [B,H,W,Cout]             */
+  float* stats_partial;       /* optional: GroupNorm partial sums of the RESULT, fused in the epilogue.
+                                 [B * rows_per_image][Cout][2] fp32 (sum, sum of squares), one row per
+                                 (128-pixel tile, 32-row warp slice); rows_per_image from
+                                 bbdm_conv_umma_geometry.  Ignored (must be NULL) when a tile spans
+                                 several images (tiles_per_image == 0).                         */
 } BbdmConvArgs;
 int bbdm_conv_umma(const BbdmConvArgs* a, void* stream);
+
+/* Tile geometry the tensor-core conv uses for an [*,H,W,*] output: pixel box TW x TH x TB (=128)
+ * and rows_per_image = 4 * tiles per image of the stats_partial buffer (0 if TB > 1). */
+int bbdm_conv_umma_geometry(int H, int W, int* TW, int* TH, int* TB, int* rows_per_image);
+
+/* mean/rstd [B,groups] of cat(t1, t2) from the per-channel partial sums the conv epilogues
+ * wrote (part2 may be NULL).  fp64 combine in a fixed order (deterministic).  hw = H*W.
+ * Replaces the separate statistics pass (bbdm_gn_stats) for conv-produced tensors. */
+int bbdm_gn_finalize_partials(const float* part1, int c1, int rows1, const float* part2, int c2,
+                              int rows2, int B, int hw, int groups, float eps, float* mean,
+                              float* rstd, void* stream);
 
 /* General fp32 direct convolution on CUDA cores (any Cin/Cout, k in {1,3}, stride 1 or 2,
  * pad k/2): stem (openaimodel.py:524), head (:690), conv-mode Downsample/Upsample (:109,150)

@@ -128,7 +128,8 @@ class EmuBackend:
 
     def conv_umma(self, *, B, H, W, Cin, Cout, taps, a_hi, a_lo, w_hi, w_lo, bias=None, Cin2=0,
                   a2_hi=None, a2_lo=None, w2_hi=None, w2_lo=None, bias2=None, residual=None,
-                  res_mode=0, out=None, out_hi=None, out_lo=None, passes=3, out_nchw_channels=0):
+                  res_mode=0, out=None, out_hi=None, out_lo=None, passes=3, out_nchw_channels=0,
+                  stats_partial=None):
         self.calls.append("conv_umma")
         assert Cin % 64 == 0 and Cout % 64 == 0 and Cin2 % 64 == 0 and W >= 4
         a = self._planes(a_hi, a_lo).reshape(B, H, W, Cin)
@@ -143,12 +144,44 @@ class EmuBackend:
             o = o + O.op_resample(residual.reshape(B, H // 2, W // 2, Cout), 1)
         elif res_mode == 3:
             o = o + O.op_resample(residual.reshape(B, H * 2, W * 2, Cout), 2)
+        if stats_partial is not None:
+            # same contract as the kernel: rows of per-channel (sum, sum sq); here all in row 0
+            rows = stats_partial.shape[0] // B
+            assert rows == self.conv_geometry(H, W)[3] and rows > 0
+            sp = stats_partial.view(B, rows, Cout, 2)
+            sp.zero_()
+            sp[:, 0, :, 0] = o.reshape(B, -1, Cout).sum(1)
+            sp[:, 0, :, 1] = (o.reshape(B, -1, Cout) ** 2).sum(1)
         if out_nchw_channels:
             out.copy_(o[..., :out_nchw_channels].permute(0, 3, 1, 2))
         elif out is not None:
             out.copy_(o.reshape(out.shape))
         if out_hi is not None:
             self._write_split(o.reshape(out_hi.shape), out_hi, out_lo)
+
+    def conv_geometry(self, H, W):
+        p2f = lambda x: 1 << (x.bit_length() - 1)
+        p2c = lambda x: 1 << (x - 1).bit_length()
+        tw = min(16, p2f(W))
+        th = min(128 // tw, p2c(H))
+        tb = 128 // (tw * th)
+        rows = 4 * (-(-W // tw)) * (-(-H // th)) if tb == 1 else 0
+        return tw, th, tb, rows
+
+    def gn_finalize_partials(self, part1, rows1, part2, rows2, B, hw, groups, eps, mean, rstd):
+        self.calls.append("gn_finalize_partials")
+        ch = [part1.view(B, rows1, -1, 2).double().sum(1)]
+        if part2 is not None:
+            ch.append(part2.view(B, rows2, -1, 2).double().sum(1))
+        s = torch.cat(ch, dim=1)                               # [B, C, 2]
+        assert not torch.isnan(s).any()
+        C = s.shape[1]
+        sg = s.view(B, groups, C // groups, 2).sum(2)
+        n = hw * (C // groups)
+        m = sg[..., 0] / n
+        var = (sg[..., 1] / n - m * m).clamp_min(0)
+        mean.copy_(m.float())
+        rstd.copy_((1.0 / torch.sqrt(var + eps)).float())
 
     def conv_direct(self, src, w_packed, bias, residual, out, Cout, k, stride=1):
         self.calls.append("conv_direct")

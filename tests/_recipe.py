@@ -43,6 +43,20 @@ UNET_CONFIGS = {
                          use_scale_shift_norm=False, resblock_updown=False,
                          use_new_attention_order=True, use_spatial_transformer=False,
                          context_dim=None, condition_key="nocond"),
+    # BASELINE configs[2..4] UNets (LBBDM-f4 / f8-variant / f16-variant):
+    # 64x64 latents, condition_key nocond; f16 has attention at ds=4 (6 AttentionBlocks, T=256)
+    "lbbdm_f4": dict(image_size=64, in_channels=3, model_channels=128, out_channels=3, num_res_blocks=2,
+                     attention_resolutions=(32, 16, 8), channel_mult=(1, 4, 8), conv_resample=True, dims=2,
+                     num_heads=8, num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True,
+                     use_spatial_transformer=False, context_dim=None, condition_key="nocond"),
+    "lbbdm_f8": dict(image_size=64, in_channels=4, model_channels=128, out_channels=4, num_res_blocks=2,
+                     attention_resolutions=(32, 16, 8), channel_mult=(1, 4, 8), conv_resample=True, dims=2,
+                     num_heads=8, num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True,
+                     use_spatial_transformer=False, context_dim=None, condition_key="nocond"),
+    "lbbdm_f16": dict(image_size=64, in_channels=16, model_channels=128, out_channels=16, num_res_blocks=2,
+                      attention_resolutions=(16, 8, 4), channel_mult=(1, 4, 8), conv_resample=True, dims=2,
+                      num_heads=8, num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True,
+                      use_spatial_transformer=False, context_dim=None, condition_key="nocond"),
     "cfg1": dict(image_size=64, in_channels=6, model_channels=128, out_channels=3,
                  num_res_blocks=2, attention_resolutions=(32, 16, 8), channel_mult=(1, 4, 8),
                  conv_resample=True, dims=2, num_heads=8, num_head_channels=64,

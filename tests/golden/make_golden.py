@@ -137,3 +137,6 @@ if __name__ == "__main__":
     unet_and_psample("mid_pixel", 2, "mid_pixel")
     if a.cfg1:
         unet_and_psample("cfg1", 4, "cfg1", bb_kw=dict(sample_step=100), with_loop=False)
+        # BASELINE configs[2..4] UNet shapes at a reduced batch (full channel widths / resolutions)
+        for name in ("lbbdm_f4", "lbbdm_f8", "lbbdm_f16"):
+            unet_and_psample(name, 2, name, with_loop=False)

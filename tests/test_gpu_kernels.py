@@ -301,3 +301,34 @@ def test_attention_split(be, B, T, heads, D, order):
     assert rel_dev(out, O.op_attention_nhwc(qkv.double(), heads, bool(order))) < 5e-5
     h, l = O.bf16_split(out.cpu())
     assert torch.equal(oh.float().cpu(), h) and torch.equal(ol.float().cpu(), l)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,c2", [(2, 16, 16, 64, 128, 0), (3, 32, 16, 128, 256, 64), (2, 12, 20, 64, 64, 0),
+                                              (2, 16, 8, 64, 640, 128)])
+def test_conv_umma_fused_groupnorm_statistics(be, B, H, W, Cin, Cout, c2):
+    """GroupNorm partial sums written by the conv epilogue + finalize == statistics of the stored
+    tensor (also for the concat of two conv outputs whose groups straddle the boundary)."""
+    def conv_with_stats(cout, seed):
+        a, w, b = rnd((B, H, W, Cin), seed), rnd((cout, Cin, 3, 3), seed + 1, 0.05), rnd((cout,), seed + 2, 0.3)
+        a_hi, a_lo = (t.to(torch.bfloat16).to(DEV) for t in O.bf16_split(a))
+        w_hi, w_lo = _pack_split(be, w)
+        rows = be.conv_geometry(H, W)[3]
+        assert rows > 0
+        part = torch.full((B * rows, cout, 2), float("nan"), device=DEV)
+        out = torch.empty((B, H, W, cout), device=DEV)
+        be.conv_umma(B=B, H=H, W=W, Cin=Cin, Cout=cout, taps=9, a_hi=a_hi, a_lo=a_lo, w_hi=w_hi, w_lo=w_lo,
+                     bias=b.to(DEV), out=out, passes=3, stats_partial=part)
+        assert not torch.isnan(part).any()
+        return out, part, rows
+
+    o1, p1, r1 = conv_with_stats(Cout, 80)
+    o2 = p2 = None
+    r2 = 0
+    if c2:
+        o2, p2, r2 = conv_with_stats(c2, 90)
+    x = o1.cpu() if o2 is None else torch.cat([o1.cpu(), o2.cpu()], 3)
+    m_want, r_want = O.op_gn_stats(x)
+    mean, rstd = torch.empty((B, 32), device=DEV), torch.empty((B, 32), device=DEV)
+    be.gn_finalize_partials(p1, r1, p2, r2, B, H * W, 32, 1e-5, mean, rstd)
+    assert (mean.cpu() - m_want).abs().max() < 3e-6 and rel_dev(rstd, r_want) < 3e-6
+    assert be.conv_geometry(4, 4)[3] == 0        # tile spans images: caller must use bbdm_gn_stats

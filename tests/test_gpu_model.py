@@ -19,6 +19,9 @@ TAGS = {
     "tiny_variant": ("tiny_variant", dict(objective="ysubx", eta=0.5)),
     "mid_pixel": ("mid_pixel", {}),
     "cfg1": ("cfg1", dict(sample_step=100)),
+    "lbbdm_f4": ("lbbdm_f4", {}),        # BASELINE configs[2] UNet (latent 64x64x3, nocond)
+    "lbbdm_f8": ("lbbdm_f8", {}),        # configs[3] UNet (64x64x4)
+    "lbbdm_f16": ("lbbdm_f16", {}),      # configs[4] UNet (64x64x16, 6 attention blocks)
 }
 
 

@@ -18,6 +18,9 @@ TAGS = {  # tag -> (unet config name, bridge kwargs used by make_golden.py)
     "tiny_variant": ("tiny_variant", dict(objective="ysubx", eta=0.5)),
     "mid_pixel": ("mid_pixel", {}),
     "cfg1": ("cfg1", dict(sample_step=100)),
+    "lbbdm_f4": ("lbbdm_f4", {}),        # BASELINE configs[2] UNet (latent 64x64x3, nocond)
+    "lbbdm_f8": ("lbbdm_f8", {}),        # configs[3] UNet (64x64x4)
+    "lbbdm_f16": ("lbbdm_f16", {}),      # configs[4] UNet (64x64x16, 6 attention blocks)
 }
 
 
@@ -106,13 +109,16 @@ def test_oracle_matches_reference_fixture(tag):
     assert rel_dev(img, g["loop8_out"]) < 1e-5
 
 
-def test_oracle_matches_cfg1_fixture():
-    """Full-size Template-BBDM UNet (237 M parameters), BASELINE configs[0]."""
-    g = load("cfg1")
-    cfg = O.unet_cfg(**UNET_CONFIGS["cfg1"])
-    sd = oracle_state("cfg1")
-    assert sum(v.numel() for v in sd.values()) == 237_094_787   # 237.09 M (SURVEY section 6)
-    out = O.unet_forward(sd, cfg, g["x"], g["t"], g["y"])
+@pytest.mark.parametrize("tag", ["cfg1", "lbbdm_f4", "lbbdm_f8", "lbbdm_f16"])
+def test_oracle_matches_full_size_fixture(tag):
+    """Full-size template UNets (237-258 M parameters): BASELINE configs[0] and the UNets of configs[2..4]."""
+    g = load(tag)
+    cfg = O.unet_cfg(**UNET_CONFIGS[tag])
+    sd = oracle_state(tag)
+    n = sum(v.numel() for v in sd.values())
+    assert n == {"cfg1": 237_094_787}.get(tag, n) and 237e6 < n < 259e6      # 237.09 M / 258.1 M (SURVEY section 6)
+    ctx = None if cfg.condition_key == "nocond" else g["y"]
+    out = O.unet_forward(sd, cfg, g["x"], g["t"], ctx)
     assert rel_dev(out, g["unet_out"]) < 2e-6
 
 
