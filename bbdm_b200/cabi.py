@@ -25,7 +25,8 @@ SYMBOLS = [
     "bbdm_abi_version", "bbdm_last_error", "bbdm_device_info", "bbdm_check_device_fault",
     "bbdm_bridge_q_sample", "bbdm_bridge_p_sample", "bbdm_bridge_p_sample_dev", "bbdm_nchw_to_nhwc_cat", "bbdm_nhwc_to_nchw",
     "bbdm_gather_rows", "bbdm_linear_f32", "bbdm_gn_stats", "bbdm_prep_operand",
-    "bbdm_pack_weight_split", "bbdm_pack_weight_split_padded", "bbdm_pack_weight_f32", "bbdm_conv_umma", "bbdm_conv_direct",
+    "bbdm_pack_weight_split", "bbdm_pack_weight_split_padded", "bbdm_pack_weight_split_taps",
+    "bbdm_pack_weight_f32", "bbdm_conv_umma", "bbdm_conv_direct",
     "bbdm_attention", "bbdm_attention_split", "bbdm_conv_umma_geometry", "bbdm_gn_finalize_partials",
 ]
 
@@ -56,7 +57,8 @@ class ConvArgs(C.Structure):
                 ("bias2", C.c_void_p),
                 ("residual", C.c_void_p), ("res_mode", C.c_int),
                 ("out", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
-                ("passes", C.c_int), ("out_nchw_channels", C.c_int), ("stats_partial", C.c_void_p)]
+                ("passes", C.c_int), ("out_nchw_channels", C.c_int), ("upsample2x", C.c_int),
+                ("stats_partial", C.c_void_p)]
 
 
 class BbdmError(RuntimeError):
@@ -92,6 +94,7 @@ def load():
     lib.bbdm_prep_operand.argtypes = [C.POINTER(PrepArgs), vp]
     lib.bbdm_pack_weight_split.argtypes = [vp, i, i, i, vp, vp, vp]
     lib.bbdm_pack_weight_split_padded.argtypes = [vp, i, i, i, i, vp, vp, vp]
+    lib.bbdm_pack_weight_split_taps.argtypes = [vp, i, i, i, vp, vp, vp]
     lib.bbdm_pack_weight_f32.argtypes = [vp, i, i, i, vp, vp]
     lib.bbdm_conv_umma.argtypes = [C.POINTER(ConvArgs), vp]
     lib.bbdm_conv_direct.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
@@ -221,10 +224,16 @@ class CudaBackend:
 
     # -- convolutions --------------------------------------------------------------------------
     def pack_weight_split(self, w, hi, lo):
-        """hi/lo: [k*k, Cout_pad, Cin] bf16 (Cout_pad >= Cout; padding rows must already be zero)."""
+        """w [Cout,Cin,k,k] -> hi/lo [k*k, Cout_pad, Cin] bf16 (Cout_pad >= Cout; padding rows pre-zeroed)."""
         Cout, Cin, k = w.shape[0], w.shape[1], (w.shape[2] if w.dim() > 2 else 1)
         check(self.lib.bbdm_pack_weight_split_padded(ptr(_req(w)), Cout, Cin, k, hi.shape[1], ptr(hi), ptr(lo),
                                                      stream()))
+        LAUNCHES["n"] += 1
+
+    def pack_weight_split_taps(self, w, hi, lo):
+        """w [Cout,Cin,taps] (any tap count) -> hi/lo [taps, Cout, Cin] bf16."""
+        Cout, Cin, taps = w.shape
+        check(self.lib.bbdm_pack_weight_split_taps(ptr(_req(w)), Cout, Cin, taps, ptr(hi), ptr(lo), stream()))
         LAUNCHES["n"] += 1
 
     def pack_weight_f32(self, w, out):
@@ -235,11 +244,11 @@ class CudaBackend:
     def conv_umma(self, *, B, H, W, Cin, Cout, taps, a_hi, a_lo, w_hi, w_lo, bias=None, Cin2=0,
                   a2_hi=None, a2_lo=None, w2_hi=None, w2_lo=None, bias2=None, residual=None,
                   res_mode=RES_NONE, out=None, out_hi=None, out_lo=None, passes=3, out_nchw_channels=0,
-                  stats_partial=None):
+                  stats_partial=None, upsample2x=False):
         a = ConvArgs(B, H, W, Cin, Cout, taps, ptr(a_hi), ptr(a_lo), ptr(w_hi), ptr(w_lo), ptr(bias),
                      Cin2, ptr(a2_hi), ptr(a2_lo), ptr(w2_hi), ptr(w2_lo), ptr(bias2),
                      ptr(residual), res_mode, ptr(out), ptr(out_hi), ptr(out_lo), passes, out_nchw_channels,
-                     ptr(stats_partial))
+                     int(upsample2x), ptr(stats_partial))
         check(self.lib.bbdm_conv_umma(C.byref(a), stream()))
         LAUNCHES["n"] += 1
 

@@ -142,6 +142,7 @@ struct ConvParams {
   int K1;           // taps * Cin/64
   int K2;           // Cin2 / 64
   int taps;
+  int up2;           // 1: fused nearest-2x upsample (4 output phases x 2x2 taps on the low-res input)
   int passes;
   int kb_per_chunk;  // K blocks accumulated in TMEM before promotion to registers
   const float* bias; const float* bias2;
@@ -213,34 +214,42 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   const uint32_t tmem_base = tmem_base_s;
 
   const int n_blocks = p.Cout / BN;
-  const int total_tiles = p.n_tiles * n_blocks;
+  const int total_tiles = p.n_tiles * n_blocks * (p.up2 ? 4 : 1);
   const int KB = p.K1 + p.K2;
 
   if (warp == 0) {
     // ================================ TMA producer ==========================================
     if (lane == 0) {
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t phase_bit = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nb = tile % n_blocks;
         int mt = tile / n_blocks;
+        int phase = 0;
+        if (p.up2) { phase = mt & 3; mt >>= 2; }
         const int tw = mt % p.tiles_w; mt /= p.tiles_w;
         const int th = mt % p.tiles_h;
         const int tb = mt / p.tiles_h;
         const int w0 = tw * p.TW, h0 = th * p.TH, b0 = tb * p.TB, n0 = nb * BN;
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1, abort_flag, p.fault, 0xE0000000ull | (unsigned)kb);
+          mbar_wait(bar_empty + 8 * stage, phase_bit ^ 1, abort_flag, p.fault, 0xE0000000ull | (unsigned)kb);
           const uint32_t sbase = tiles_base + stage * STAGE_BYTES;
           const uint32_t full = bar_full + 8 * stage;
           mbar_expect_tx(full, STAGE_BYTES);
           if (kb < p.K1) {
             const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
-            int dy = 0, dx = 0;
-            if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+            int dy = 0, dx = 0, wtap = tap;
+            if (p.up2) {
+              // output phase (a, b) = (phase>>1, phase&1); 2x2 taps (r, c) on the low-res source
+              const int r = tap >> 1, c = tap & 1;
+              dy = (phase >> 1) ? r : r - 1;
+              dx = (phase & 1) ? c : c - 1;
+              wtap = phase * 4 + tap;
+            } else if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
             tma_load_4d(sbase, &map_a_hi, full, cb * UM_BK, w0 + dx, h0 + dy, b0);
             if (PASSES == 3) tma_load_4d(sbase + OFF_ALO, &map_a_lo, full, cb * UM_BK, w0 + dx, h0 + dy, b0);
-            tma_load_3d(sbase + OFF_WHI, &map_w_hi, full, cb * UM_BK, n0, tap);
-            if (PASSES == 3) tma_load_3d(sbase + OFF_WLO, &map_w_lo, full, cb * UM_BK, n0, tap);
+            tma_load_3d(sbase + OFF_WHI, &map_w_hi, full, cb * UM_BK, n0, wtap);
+            if (PASSES == 3) tma_load_3d(sbase + OFF_WLO, &map_w_lo, full, cb * UM_BK, n0, wtap);
           } else {
             const int cb = kb - p.K1;
             tma_load_4d(sbase, &map_a2_hi, full, cb * UM_BK, w0, h0, b0);
@@ -248,7 +257,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             tma_load_3d(sbase + OFF_WHI, &map_w2_hi, full, cb * UM_BK, n0, 0);
             if (PASSES == 3) tma_load_3d(sbase + OFF_WLO, &map_w2_lo, full, cb * UM_BK, n0, 0);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase_bit ^= 1; }
         }
       }
     }
@@ -310,14 +319,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nb = tile % n_blocks;
       int mt = tile / n_blocks;
+      int phase = 0;
+      if (p.up2) { phase = mt & 3; mt >>= 2; }
       const int tw = mt % p.tiles_w; mt /= p.tiles_w;
       const int th = mt % p.tiles_h;
       const int tb = mt / p.tiles_h;
-      const int ww = tw * p.TW + row % p.TW;
-      const int hh = th * p.TH + (row / p.TW) % p.TH;
+      const int ws = tw * p.TW + row % p.TW;            // coordinates in the conv INPUT grid
+      const int hs = th * p.TH + (row / p.TW) % p.TH;
       const int bb = tb * p.TB + row / (p.TW * p.TH);
-      const bool valid = ww < p.W && hh < p.H && bb < p.B;
-      const int64_t pix = ((int64_t)bb * p.H + hh) * p.W + ww;
+      const bool valid = ws < p.W && hs < p.H && bb < p.B;
+      // output grid: same as the input, or 2x with this tile's phase offset (fused upsample)
+      const int OH = p.up2 ? 2 * p.H : p.H, OW = p.up2 ? 2 * p.W : p.W;
+      const int hh = p.up2 ? 2 * hs + (phase >> 1) : hs;
+      const int ww = p.up2 ? 2 * ws + (phase & 1) : ws;
+      const int64_t pix = ((int64_t)bb * OH + hh) * OW + ww;
       const int n0 = nb * BN + col0;
 
       float racc[COLS];
@@ -370,15 +385,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               r[j] += t.x; r[j + 1] += t.y; r[j + 2] += t.z; r[j + 3] += t.w;
             }
           } else if (p.res_mode == BBDM_RES_UP2) {
-            const float* rp = p.residual + (((int64_t)bb * (p.H >> 1) + (hh >> 1)) * (p.W >> 1) + (ww >> 1)) * p.Cout + nc;
+            const float* rp = p.residual + (((int64_t)bb * (OH >> 1) + (hh >> 1)) * (OW >> 1) + (ww >> 1)) * p.Cout + nc;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 t = ld_f4(rp + j);
               r[j] += t.x; r[j + 1] += t.y; r[j + 2] += t.z; r[j + 3] += t.w;
             }
           } else if (p.res_mode == BBDM_RES_DOWN2) {
-            const int64_t W2 = (int64_t)p.W * 2;
-            const float* rp = p.residual + (((int64_t)bb * p.H * 2 + hh * 2) * W2 + ww * 2) * p.Cout + nc;
+            const int64_t W2 = (int64_t)OW * 2;
+            const float* rp = p.residual + (((int64_t)bb * OH * 2 + hh * 2) * W2 + ww * 2) * p.Cout + nc;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 t0 = ld_f4(rp + j), t1 = ld_f4(rp + p.Cout + j);
@@ -394,7 +409,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (nc + j < p.out_nchw_c)
-                p.out[(((int64_t)bb * p.out_nchw_c + nc + j) * p.H + hh) * p.W + ww] = r[j];
+                p.out[(((int64_t)bb * p.out_nchw_c + nc + j) * OH + hh) * OW + ww] = r[j];
           } else if (p.out) {
             float* op = p.out + pix * p.Cout + nc;
 #pragma unroll
@@ -418,7 +433,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             for (int j = 0; j < 32; ++j) { if (!valid) r[j] = 0.f; sq[j] = r[j] * r[j]; }
             warp_colsum32(r, lane);
             warp_colsum32(sq, lane);
-            const int64_t prow = ((int64_t)tb * p.tiles_w * p.tiles_h + th * p.tiles_w + tw) * 4 + q;
+            const int64_t prow = (((int64_t)tb * p.tiles_w * p.tiles_h + th * p.tiles_w + tw) * (p.up2 ? 4 : 1) + phase) * 4 + q;
             *reinterpret_cast<float2*>(p.stats + (prow * p.Cout + nc + lane) * 2) = make_float2(r[0], sq[0]);
           }
         }
@@ -514,6 +529,7 @@ static void tile_geometry(int H, int W, int* TW, int* TH, int* TB) {
   *TB = UM_BM / (*TW * *TH);
 }
 
+// (for an upsample2x conv call this with the INPUT H, W and multiply rows_per_image by 4)
 extern "C" int bbdm_conv_umma_geometry(int H, int W, int* TW, int* TH, int* TB, int* rows_per_image) {
   BBDM_REQUIRE(H > 0 && W >= 4, "conv_umma_geometry: need H > 0, W >= 4");
   int tw, th, tb;
@@ -528,7 +544,8 @@ extern "C" int bbdm_conv_umma_geometry(int H, int W, int* TW, int* TH, int* TB, 
 extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   BBDM_REQUIRE(a != nullptr, "conv_umma: null args");
   BBDM_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0, "conv_umma: bad spatial shape");
-  BBDM_REQUIRE(a->taps == 1 || a->taps == 9, "conv_umma: taps must be 1 or 9 (got %d)", a->taps);
+  BBDM_REQUIRE(a->taps == 1 || a->taps == 9 || (a->upsample2x && a->taps == 4), "conv_umma: taps must be 1 or 9 (got %d)", a->taps);
+  BBDM_REQUIRE(!a->upsample2x || (a->taps == 4 && a->Cin2 == 0), "conv_umma: upsample2x needs the 16 phase taps and no fused 1x1");
   BBDM_REQUIRE(a->Cin > 0 && a->Cin % 64 == 0, "conv_umma: Cin %% 64 != 0 (Cin=%d)", a->Cin);
   BBDM_REQUIRE(a->Cout > 0 && a->Cout % 64 == 0, "conv_umma: Cout %% 64 != 0 (Cout=%d)", a->Cout);
   BBDM_REQUIRE(a->Cin2 >= 0 && a->Cin2 % 64 == 0, "conv_umma: Cin2 %% 64 != 0 (Cin2=%d)", a->Cin2);
@@ -538,7 +555,7 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   BBDM_REQUIRE(a->out || (a->out_hi && a->out_lo), "conv_umma: no output");
   BBDM_REQUIRE((a->out_hi == nullptr) == (a->out_lo == nullptr), "conv_umma: out hi/lo must come in pairs");
   BBDM_REQUIRE(a->res_mode >= 0 && a->res_mode <= 3 && (a->res_mode == 0 || a->residual), "conv_umma: bad residual");
-  if (a->res_mode == BBDM_RES_UP2) BBDM_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0, "conv_umma: RES_UP2 needs even H, W");
+  if (a->res_mode == BBDM_RES_UP2 && !a->upsample2x) BBDM_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0, "conv_umma: RES_UP2 needs even H, W");
   BBDM_REQUIRE(a->W >= 4, "conv_umma: W < 4 not supported (use conv_direct)");
 
   ConvParams p;
@@ -552,6 +569,7 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   p.K1 = a->taps * p.kb_per_tap;
   p.K2 = a->Cin2 / 64;
   p.taps = a->taps;
+  p.up2 = a->upsample2x ? 1 : 0;
   p.passes = a->passes;
   p.kb_per_chunk = a->passes == 3 ? 4 : 8;
   p.bias = a->bias; p.bias2 = a->Cin2 ? a->bias2 : nullptr;
@@ -571,8 +589,9 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   int rc;
   if ((rc = make_act_map(&maps[0], a->a_hi, a->B, a->H, a->W, a->Cin, p.TW, p.TH, p.TB))) return rc;
   if ((rc = make_act_map(&maps[1], a->passes == 3 ? a->a_lo : a->a_hi, a->B, a->H, a->W, a->Cin, p.TW, p.TH, p.TB))) return rc;
-  if ((rc = make_w_map(&maps[2], a->w_hi, a->taps, a->Cout, a->Cin, BN))) return rc;
-  if ((rc = make_w_map(&maps[3], a->passes == 3 ? a->w_lo : a->w_hi, a->taps, a->Cout, a->Cin, BN))) return rc;
+  const int wtaps = a->upsample2x ? 16 : a->taps;
+  if ((rc = make_w_map(&maps[2], a->w_hi, wtaps, a->Cout, a->Cin, BN))) return rc;
+  if ((rc = make_w_map(&maps[3], a->passes == 3 ? a->w_lo : a->w_hi, wtaps, a->Cout, a->Cin, BN))) return rc;
   if (a->Cin2) {
     if ((rc = make_act_map(&maps[4], a->a2_hi, a->B, a->H, a->W, a->Cin2, p.TW, p.TH, p.TB))) return rc;
     if ((rc = make_act_map(&maps[5], a->passes == 3 ? a->a2_lo : a->a2_hi, a->B, a->H, a->W, a->Cin2, p.TW, p.TH, p.TB))) return rc;
@@ -581,7 +600,7 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   } else {
     maps[4] = maps[0]; maps[5] = maps[1]; maps[6] = maps[2]; maps[7] = maps[3];
   }
-  const int64_t total = (int64_t)p.n_tiles * (a->Cout / BN);
+  const int64_t total = (int64_t)p.n_tiles * (a->Cout / BN) * (p.up2 ? 4 : 1);
   BBDM_REQUIRE(total < (1ll << 30), "conv_umma: too many tiles");
   const int grid = (int)(total < num_sms() ? total : num_sms());
   cudaStream_t s = (cudaStream_t)stream;

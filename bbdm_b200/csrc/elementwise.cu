@@ -314,6 +314,15 @@ int bbdm_pack_weight_split_padded(const float* w, int Cout, int Cin, int k, int 
   return BBDM_OK;
 }
 
+int bbdm_pack_weight_split_taps(const float* w, int Cout, int Cin, int taps, void* w_hi, void* w_lo, void* stream) {
+  BBDM_REQUIRE(w && w_hi && w_lo && Cout > 0 && Cin > 0 && taps > 0, "pack_weight_split_taps: bad args");
+  const int64_t n = (int64_t)taps * Cout * Cin;
+  pack_weight_split_kernel<<<grid_for(n, 256, num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(
+      w, Cout, Cin, taps, Cout, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo);
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
 int bbdm_pack_weight_split(const float* w, int Cout, int Cin, int k, void* w_hi, void* w_lo, void* stream) {
   return bbdm_pack_weight_split_padded(w, Cout, Cin, k, Cout, w_hi, w_lo, stream);
 }

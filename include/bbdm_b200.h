@@ -162,6 +162,10 @@ int bbdm_pack_weight_split(const float* w, int Cout, int Cin, int k, void* w_hi,
  * tensor-core kernel with an N tile of 64. */
 int bbdm_pack_weight_split_padded(const float* w, int Cout, int Cin, int k, int Cout_pad,
                                   void* w_hi, void* w_lo, void* stream);
+/* General tap count: w [Cout][Cin][taps] fp32 -> hi/lo bf16 [taps][Cout][Cin] (used for the 16
+ * phase taps of the fused-upsample conv, BbdmConvArgs.upsample2x). */
+int bbdm_pack_weight_split_taps(const float* w, int Cout, int Cin, int taps, void* w_hi, void* w_lo,
+                                void* stream);
 int bbdm_pack_weight_f32(const float* w, int Cout, int Cin, int k, float* out, void* stream);
 
 enum { BBDM_RES_NONE = 0, BBDM_RES_SAME = 1, BBDM_RES_UP2 = 2, BBDM_RES_DOWN2 = 3 };
@@ -194,6 +198,13 @@ typedef struct {
   int out_nchw_channels;      /* > 0: `out` is NCHW [B, out_nchw_channels, H, W] and only the first
                                  out_nchw_channels (<= Cout) couts are stored (UNet head, replaces
                                  the final layout change); 0: NHWC [B,H,W,Cout]             */
+  int upsample2x;             /* 1: the conv input is the nearest-2x upsampling of A (openaimodel.py:118,
+                                 212-214) WITHOUT materialising it: A is the low-res tensor [B,H,W,Cin],
+                                 the output is [B,2H,2W,Cout]; each output phase (y%2, x%2) is a 2x2
+                                 conv whose taps are sums of the 3x3 taps (w_hi/w_lo: [16][Cout][Cin],
+                                 index phase*4 + r*2 + c; taps = 4) -- 2.25x fewer MACs than the 3x3
+                                 on the upsampled tensor.  residual/res_mode address the OUTPUT grid;
+                                 stats_partial then has 4x the rows.                               */
   float* stats_partial;       /* optional: GroupNorm partial sums of the RESULT, fused in the epilogue.
                                  [B * rows_per_image][Cout][2] fp32 (sum, sum of squares), one row per
                                  (128-pixel tile, 32-row warp slice); rows_per_image from

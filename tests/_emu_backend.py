@@ -129,8 +129,11 @@ class EmuBackend:
     def conv_umma(self, *, B, H, W, Cin, Cout, taps, a_hi, a_lo, w_hi, w_lo, bias=None, Cin2=0,
                   a2_hi=None, a2_lo=None, w2_hi=None, w2_lo=None, bias2=None, residual=None,
                   res_mode=0, out=None, out_hi=None, out_lo=None, passes=3, out_nchw_channels=0,
-                  stats_partial=None):
+                  stats_partial=None, upsample2x=False):
         self.calls.append("conv_umma")
+        if upsample2x:
+            return self._conv_up2(B, H, W, Cin, Cout, a_hi, a_lo, w_hi, w_lo, bias, residual, res_mode, out,
+                                  stats_partial)
         assert Cin % 64 == 0 and Cout % 64 == 0 and Cin2 % 64 == 0 and W >= 4
         a = self._planes(a_hi, a_lo).reshape(B, H, W, Cin)
         assert not torch.isnan(a).any()
@@ -158,6 +161,41 @@ class EmuBackend:
             out.copy_(o.reshape(out.shape))
         if out_hi is not None:
             self._write_split(o.reshape(out_hi.shape), out_hi, out_lo)
+
+    def _conv_up2(self, B, H, W, Cin, Cout, a_hi, a_lo, w_hi, w_lo, bias, residual, res_mode, out, stats_partial):
+        """The kernel's phase formulation, literally: 4 phases x 2x2 taps on the low-res input."""
+        a = self._planes(a_hi, a_lo).reshape(B, H, W, Cin)
+        w = (w_hi.float() + w_lo.float())                     # [16, Cout, Cin]
+        ap = F.pad(a, (0, 0, 1, 1, 1, 1))                     # zero pad H and W by 1
+        o = torch.zeros(B, 2 * H, 2 * W, Cout)
+        for ph in range(4):
+            pa, pb = ph >> 1, ph & 1
+            acc = torch.zeros(B, H, W, Cout)
+            for t in range(4):
+                r, c = t >> 1, t & 1
+                dy = r if pa else r - 1
+                dx = c if pb else c - 1
+                src = ap[:, 1 + dy:1 + dy + H, 1 + dx:1 + dx + W, :]
+                acc = acc + src @ w[ph * 4 + t].T
+            o[:, pa::2, pb::2, :] = acc
+        if bias is not None:
+            o = o + bias
+        if res_mode == 1:
+            o = o + residual.reshape(B, 2 * H, 2 * W, Cout)
+        elif res_mode == 2:
+            o = o + O.op_resample(residual.reshape(B, H, W, Cout), 1)
+        if stats_partial is not None:
+            rows = stats_partial.shape[0] // B
+            assert rows == 4 * self.conv_geometry(H, W)[3] and rows > 0
+            sp = stats_partial.view(B, rows, Cout, 2)
+            sp.zero_()
+            sp[:, 0, :, 0] = o.reshape(B, -1, Cout).sum(1)
+            sp[:, 0, :, 1] = (o.reshape(B, -1, Cout) ** 2).sum(1)
+        out.copy_(o)
+
+    def pack_weight_split_taps(self, w, hi, lo):
+        self.calls.append("pack_weight_split_taps")
+        self._write_split(w.permute(2, 0, 1), hi, lo)
 
     def conv_geometry(self, H, W):
         p2f = lambda x: 1 << (x.bit_length() - 1)

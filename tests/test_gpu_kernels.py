@@ -332,3 +332,36 @@ def test_conv_umma_fused_groupnorm_statistics(be, B, H, W, Cin, Cout, c2):
     be.gn_finalize_partials(p1, r1, p2, r2, B, H * W, 32, 1e-5, mean, rstd)
     assert (mean.cpu() - m_want).abs().max() < 3e-6 and rel_dev(rstd, r_want) < 3e-6
     assert be.conv_geometry(4, 4)[3] == 0        # tile spans images: caller must use bbdm_gn_stats
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,res", [(2, 8, 8, 64, 64, False), (2, 16, 16, 128, 256, True), (1, 12, 20, 64, 128, False),
+                                                (3, 4, 4, 256, 256, True)])
+def test_conv_umma_fused_upsample(be, B, H, W, Cin, Cout, res):
+    """nearest-2x + 3x3 conv as 4 phases x 2x2 taps on the low-res operand == conv on the upsampled tensor."""
+    from bbdm_b200.weights import upsample_phase_weights
+    a, w, b = rnd((B, H, W, Cin), 100), rnd((Cout, Cin, 3, 3), 101, 0.03), rnd((Cout,), 102, 0.1)
+    a_hi, a_lo = (t.to(torch.bfloat16).to(DEV) for t in O.bf16_split(a))
+    wp = upsample_phase_weights(w).to(DEV)
+    hi = torch.empty((16, Cout, Cin), dtype=torch.bfloat16, device=DEV)
+    lo = torch.empty_like(hi)
+    be.pack_weight_split_taps(wp, hi, lo)
+    a_val = sum(O.bf16_split(a)).double()                       # the value the planes carry
+    want = O.op_conv_nhwc(O.op_resample(a_val, 1), w.double(), b.double())
+    r = None
+    if res:
+        r = rnd((B, H, W, Cout), 103)
+        want = want + O.op_resample(r.double(), 1)
+    rows = 4 * be.conv_geometry(H, W)[3]
+    part = torch.full((B * rows, Cout, 2), float("nan"), device=DEV) if rows else None
+    out = torch.full((B, 2 * H, 2 * W, Cout), float("nan"), device=DEV)
+    be.conv_umma(B=B, H=H, W=W, Cin=Cin, Cout=Cout, taps=4, a_hi=a_hi, a_lo=a_lo, w_hi=hi, w_lo=lo, bias=b.to(DEV),
+                 residual=None if r is None else r.to(DEV), res_mode=2 if res else 0, out=out, passes=3,
+                 upsample2x=True, stats_partial=part)
+    be.check_fault()
+    assert not torch.isnan(out).any()
+    assert rel_dev(out, want) < 3e-5           # weights are re-split after the tap sums: 2^-17-level difference
+    if part is not None:
+        mean, rstd = torch.empty((B, 32), device=DEV), torch.empty((B, 32), device=DEV)
+        be.gn_finalize_partials(part, rows, None, 0, B, 4 * H * W, 32, 1e-5, mean, rstd)
+        m_want, r_want = O.op_gn_stats(out.cpu())
+        assert (mean.cpu() - m_want).abs().max() < 3e-6 and rel_dev(rstd, r_want) < 3e-6
