@@ -27,7 +27,7 @@ SYMBOLS = [
     "bbdm_gather_rows", "bbdm_linear_f32", "bbdm_gn_stats", "bbdm_prep_operand",
     "bbdm_pack_weight_split", "bbdm_pack_weight_split_padded", "bbdm_pack_weight_split_taps",
     "bbdm_pack_weight_f32", "bbdm_conv_umma", "bbdm_conv_direct",
-    "bbdm_attention", "bbdm_attention_split", "bbdm_conv_umma_geometry", "bbdm_gn_finalize_partials",
+    "bbdm_attention", "bbdm_attention_split", "bbdm_attention_tc", "bbdm_conv_umma_geometry", "bbdm_gn_finalize_partials",
 ]
 
 
@@ -102,6 +102,7 @@ def load():
     lib.bbdm_conv_umma_geometry.argtypes = [i, i, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     lib.bbdm_gn_finalize_partials.argtypes = [vp, i, i, vp, i, i, i, i, i, f, vp, vp, vp]
     lib.bbdm_attention_split.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp]
+    lib.bbdm_attention_tc.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp]
     for s in SYMBOLS:
         fn = getattr(lib, s)
         if s not in ("bbdm_last_error",):
@@ -283,6 +284,12 @@ class CudaBackend:
         check(self.lib.bbdm_attention_split(ptr(_req(qkv_hi, torch.bfloat16)), ptr(_req(qkv_lo, torch.bfloat16)),
                                             B, T, C3 // 3, heads, order, ptr(out_f32), ptr(out_hi), ptr(out_lo),
                                             stream()))
+        LAUNCHES["n"] += 1
+
+    def attention_tc(self, qkv_hi, qkv_lo, heads, order, out_f32=None, out_hi=None, out_lo=None):
+        B, T, C3 = qkv_hi.shape
+        check(self.lib.bbdm_attention_tc(ptr(_req(qkv_hi, torch.bfloat16)), ptr(_req(qkv_lo, torch.bfloat16)),
+                                         B, T, C3 // 3, heads, order, ptr(out_f32), ptr(out_hi), ptr(out_lo), stream()))
         LAUNCHES["n"] += 1
 
     def check_fault(self):

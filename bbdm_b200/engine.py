@@ -70,6 +70,7 @@ class UNetEngine:
         self._gn_ws = None
         self.num_timesteps = 1000
         self._geom_cache = {}
+        self.attention_impl = "tcgen05"      # "mma.sync" selects bbdm_attention_split for head_dim 64 too
         self.generation = 0          # bumps whenever cache/parameter ADDRESSES change (graphs key on it)
 
     # ------------------------------------------------------------------------------ weights
@@ -380,8 +381,10 @@ class UNetEngine:
         order = 1 if m.new_order else 0
         if umma:
             o_hi, o_lo = pool.get(x.shape, torch.bfloat16), pool.get(x.shape, torch.bfloat16)
-            be.attention_split(q_hi.view(B, T, 3 * Cc), q_lo.view(B, T, 3 * Cc), heads, order,
-                               None, o_hi.view(B, T, Cc), o_lo.view(B, T, Cc))
+            # head_dim 64 (all templates): warp-specialised tcgen05 kernel; else the mma.sync one
+            attn = be.attention_tc if (hd == 64 and self.attention_impl == "tcgen05") else be.attention_split
+            attn(q_hi.view(B, T, 3 * Cc), q_lo.view(B, T, 3 * Cc), heads, order,
+                 None, o_hi.view(B, T, Cc), o_lo.view(B, T, Cc))
         else:
             o_f32 = pool.get(x.shape)
             be.attention(qkv.view(B, T, 3 * Cc), heads, order, o_f32.view(B, T, Cc), None, None)

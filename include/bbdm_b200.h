@@ -251,6 +251,14 @@ int bbdm_attention(const float* qkv, int B, int T, int C, int heads, int order,
 int bbdm_attention_split(const void* qkv_hi, const void* qkv_lo, int B, int T, int C, int heads,
                          int order, float* out_f32, void* out_hi, void* out_lo, void* stream);
 
+/* The same computation as a FlashAttention-style WARP-SPECIALISED tcgen05 kernel (head_dim 64):
+ * TMA-staged Q / K / V tiles, S = Q K^T and O = P V on tcgen05.mma with TMEM accumulators (V
+ * consumed as an MN-major operand, P written to shared memory in the UMMA swizzle by the softmax
+ * warps), one query row per softmax thread, fp32 register accumulation of O with the
+ * online-softmax rescale.  Returns BBDM_E_UNSUPPORTED for other head dims. */
+int bbdm_attention_tc(const void* qkv_hi, const void* qkv_lo, int B, int T, int C, int heads,
+                      int order, float* out_f32, void* out_hi, void* out_lo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -244,5 +244,10 @@ class EmuBackend:
         self.calls.append("attention_split")
         self.attention(self._planes(qkv_hi, qkv_lo), heads, order, out_f32, out_hi, out_lo)
 
+    def attention_tc(self, qkv_hi, qkv_lo, heads, order, out_f32=None, out_hi=None, out_lo=None):
+        self.calls.append("attention_tc")
+        assert qkv_hi.shape[2] // 3 // heads == 64
+        self.attention(self._planes(qkv_hi, qkv_lo), heads, order, out_f32, out_hi, out_lo)
+
     def check_fault(self):
         pass

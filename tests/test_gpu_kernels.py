@@ -365,3 +365,25 @@ def test_conv_umma_fused_upsample(be, B, H, W, Cin, Cout, res):
         be.gn_finalize_partials(part, rows, None, 0, B, 4 * H * W, 32, 1e-5, mean, rstd)
         m_want, r_want = O.op_gn_stats(out.cpu())
         assert (mean.cpu() - m_want).abs().max() < 3e-6 and rel_dev(rstd, r_want) < 3e-6
+
+
+@pytest.mark.parametrize("B,T,heads,order", [(1, 128, 1, 0), (2, 256, 4, 0), (1, 1024, 2, 1), (1, 100, 2, 1), (1, 4096, 2, 0),
+                                              (2, 200, 3, 0)])
+def test_attention_tc(be, B, T, heads, order):
+    """Warp-specialised tcgen05 attention (head_dim 64) against the exact result for the planes' value."""
+    D = 64
+    C = heads * D
+    qkv = rnd((B, T, 3 * C), 62, 1.2)
+    hi, lo = O.bf16_split(qkv)
+    want = O.op_attention_nhwc((hi + lo).double(), heads, bool(order))
+    out = torch.full((B, T, C), float("nan"), device=DEV)
+    oh = torch.empty((B, T, C), dtype=torch.bfloat16, device=DEV)
+    ol = torch.empty_like(oh)
+    be.attention_tc(hi.to(torch.bfloat16).to(DEV), lo.to(torch.bfloat16).to(DEV), heads, order,
+                    out_f32=out, out_hi=oh, out_lo=ol)
+    torch.cuda.synchronize()
+    be.check_fault()
+    assert not torch.isnan(out).any()
+    assert rel_dev(out, want) < 2e-5, rel_dev(out, want)
+    h, l = O.bf16_split(out.cpu())
+    assert torch.equal(oh.float().cpu(), h) and torch.equal(ol.float().cpu(), l)
