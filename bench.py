@@ -46,6 +46,29 @@ CONFIGS = {
                  batch=4, size=64, channels=3, sample_step=100,
                  name="pixel-BBDM 64x64 RGB, batch 4, 100 steps (BASELINE configs[0])",
                  flops_per_step=0.991e12),
+    # BASELINE configs[2..4]: the latent UNets (VQGAN ends excluded: the frozen reference module, out of
+    # the measured path).  These are parity-test cases; bench lines for them are informational.
+    "cfg3": dict(unet=dict(image_size=64, in_channels=3, model_channels=128, out_channels=3, num_res_blocks=2,
+                           attention_resolutions=(32, 16, 8), channel_mult=(1, 4, 8), conv_resample=True, dims=2,
+                           num_heads=8, num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True,
+                           use_spatial_transformer=False, context_dim=None, condition_key="nocond"),
+                 batch=32, size=64, channels=3, sample_step=200,
+                 name="LBBDM-f4 latent 64x64x3, batch 32 per GPU, UNet sampling step (BASELINE configs[2] shape)",
+                 flops_per_step=7.93e12),
+    "cfg4": dict(unet=dict(image_size=64, in_channels=4, model_channels=128, out_channels=4, num_res_blocks=2,
+                           attention_resolutions=(32, 16, 8), channel_mult=(1, 4, 8), conv_resample=True, dims=2,
+                           num_heads=8, num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True,
+                           use_spatial_transformer=False, context_dim=None, condition_key="nocond"),
+                 batch=64, size=64, channels=4, sample_step=200,
+                 name="LBBDM-f8 latent 64x64x4, batch 64, sharded sampling step (BASELINE configs[3] shape)",
+                 flops_per_step=15.86e12),
+    "cfg5": dict(unet=dict(image_size=64, in_channels=16, model_channels=128, out_channels=16, num_res_blocks=2,
+                           attention_resolutions=(16, 8, 4), channel_mult=(1, 4, 8), conv_resample=True, dims=2,
+                           num_heads=8, num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True,
+                           use_spatial_transformer=False, context_dim=None, condition_key="nocond"),
+                 batch=8, size=64, channels=16, sample_step=200,
+                 name="LBBDM-f16 latent 64x64x16, batch 8, attention-heavy UNet (BASELINE configs[4] shape)",
+                 flops_per_step=2.08e12),
 }
 METRIC = "denoising-steps/sec (UNet fwd) at 256^2 pixel-BBDM"
 
@@ -152,11 +175,22 @@ def cpu_step_time(cfg, sample_batch, n_steps, threads):
     return statistics.mean(times[1:]) if n_steps else times[0]
 
 
+def host_threads():
+    """All the host threads torch's CPU kernels can use productively: physical cores (SMT siblings
+    only slow the fp32 conv/GEMM kernels down)."""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+    except Exception:
+        n = None
+    return int(n or os.cpu_count() or 1)
+
+
 def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     sb = 1 if cfg["batch"] > 4 else cfg["batch"]
     per = cpu_step_time(cfg, sb, max(1, args.steps), threads)
     scale = cfg["batch"] / sb
@@ -184,6 +218,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
     ap.add_argument("--precision", default="split3", choices=["split3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="also time CUDA-graph replays of the captured sampling step")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
@@ -239,6 +274,9 @@ def main():
     y = y_host.to(dev)
     n_sched = len(net.steps)
 
+    def ctx_of(t):
+        return None if cfg["unet"]["condition_key"] == "nocond" else t
+
     def barrier():
         if dist is not None:
             dist.barrier()
@@ -254,7 +292,7 @@ def main():
     # ---- device-resident timing: K consecutive steps of the loop ---------------------------------
     x = x_host.to(dev)
     for i in range(args.warmup):
-        x, _ = net.p_sample(x, y, y, 5 + i)
+        x, _ = net.p_sample(x, y, ctx_of(y), 5 + i)
     barrier()
     clocks = ClockSampler(local)
     clocks.start()
@@ -265,7 +303,7 @@ def main():
     t_wall0 = time.time()
     e0.record()
     for i in range(args.steps):
-        x, _ = net.p_sample(x, y, y, (10 + i) % (n_sched - 1))
+        x, _ = net.p_sample(x, y, ctx_of(y), (10 + i) % (n_sched - 1))
     e1.record()
     barrier()
     t_wall1 = time.time()
@@ -276,7 +314,7 @@ def main():
     for i in range(2):
         xd = x_host.to(dev, non_blocking=True)
         yd = y_host.to(dev, non_blocking=True)
-        o, _ = net.p_sample(xd, yd, yd, 7)
+        o, _ = net.p_sample(xd, yd, ctx_of(yd), 7)
         out_host.copy_(o, non_blocking=True)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -284,7 +322,7 @@ def main():
     for i in range(args.steps):
         xd = x_host.to(dev, non_blocking=True)
         yd = y_host.to(dev, non_blocking=True)
-        o, _ = net.p_sample(xd, yd, yd, (10 + i) % (n_sched - 1))       # the public API call of the loop body
+        o, _ = net.p_sample(xd, yd, ctx_of(yd), (10 + i) % (n_sched - 1))   # the public API call of the loop body
         out_host.copy_(o, non_blocking=True)
         x_host.copy_(out_host)                                           # next step's host-side input
     e3.record()
@@ -293,9 +331,29 @@ def main():
     ms_e2e = max_over_ranks(e2.elapsed_time(e3)) / args.steps
     net._bridge.backend().check_fault()
 
+    # ---- CUDA-graph replay of the captured step (what p_sample_loop / sample() executes) ------------
+    graph_ms = None
+    if args.graph:
+        st = net._bridge._step_graph(y, ctx_of(y), False)
+        st["x"].copy_(x)
+        st["coef"].copy_(net._bridge.coef_table()[10].to(dev))
+        st["t"].fill_(int(net.steps[10]))
+        for _ in range(2):
+            st["noise"].normal_()
+            st["graph"].replay()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            st["noise"].normal_()
+            st["graph"].replay()
+        g1.record()
+        barrier()
+        graph_ms = max_over_ranks(g0.elapsed_time(g1)) / args.steps
+
     # ---- roofline of the dominant kernel family (tcgen05 implicit-GEMM conv), one profiled step -----
     ProfilingBackend.record, ProfilingBackend.events = True, []
-    x2, _ = net.p_sample(x, y, y, 20)
+    x2, _ = net.p_sample(x, y, ctx_of(y), 20)
     torch.cuda.synchronize()
     ProfilingBackend.record = False
     conv_ms = sum(a.elapsed_time(b) for a, b, _ in ProfilingBackend.events)
@@ -304,8 +362,12 @@ def main():
     peaks, peak_src = load_peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     achieved_tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    if os.path.exists(tp):        # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch_mean")
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None,
+                "frac": achieved_tf / peak_tf, "traffic": traffic,
                 "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM conv, %d launches/step)" % n_conv,
                 "algorithmic_flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms,
                 "share_of_step": conv_ms / ms_dev if ms_dev else None,
@@ -316,7 +378,7 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = host_threads()
             sb = 1 if B > 4 else B
             per = cpu_step_time(cfg, sb, 1, threads)
             scale = B / sb
@@ -330,7 +392,10 @@ def main():
                 "dtype": "bf16x3 (split-bf16 tensor-core products, fp32 accumulate: fp32-class)" if args.precision == "split3" else "bf16",
                 "data": "synthetic",
                 "config": {"workload": cfg["name"], "batch_per_gpu": B, "image": [C, S, S], "parallelism": f"dp{world} (sharded sampling, no collective)",
-                           "precision": args.precision, "l2": "inputs larger than L2 (activations 0.5-1.3 GB per tensor)",
+                           "precision": args.precision,
+                           "l2": "working set larger than L2: every step streams the 0.95 GB of split-bf16 weights"
+                                 + (" and 0.5-1.3 GB activation tensors" if args.config == "cfg2" else ""),
+                           "graph_replay_ms_per_step": graph_ms,
                            "img_steps_per_s": world * B * 1e3 / ms_dev,
                            "unet_tflops_per_s": world * cfg["flops_per_step"] / (ms_dev * 1e-3) / 1e12},
                 "e2e": {"value": world * 1e3 / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": 2 * nbytes,
