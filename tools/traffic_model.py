@@ -71,6 +71,9 @@ class Rec:
         self._add("attention", nbytes(qh, ql, out_f32, out_hi, out_lo), 4.0 * B * (C3 // 3) * T * T)
 
 
+Rec.attention_tc = Rec.attention_split
+
+
 def main(cfg_name="cfg2"):
     cfg = bench.CONFIGS[cfg_name]
     unet = UNetModel(**cfg["unet"])
