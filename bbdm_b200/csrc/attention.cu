@@ -17,13 +17,7 @@ __device__ __forceinline__ void mma_bf16_16816(float* d, const uint32_t* a, uint
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 hx, lx, hy, ly;
-  split_bf16(x, hx, lx);
-  split_bf16(y, hy, ly);
-  hi = pack_bf16x2(hx, hy);
-  lo = pack_bf16x2(lx, ly);
-}
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) { split2x(x, y, hi, lo); }
 
 template <int D>
 __global__ void __launch_bounds__(128)

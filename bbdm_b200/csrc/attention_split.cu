@@ -39,13 +39,7 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void split2p(float x, float y, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 hx, lx, hy, ly;
-  split_bf16(x, hx, lx);
-  split_bf16(y, hy, ly);
-  hi = pack_bf16x2(hx, hy);
-  lo = pack_bf16x2(lx, ly);
-}
+__device__ __forceinline__ void split2p(float x, float y, uint32_t& hi, uint32_t& lo) { split2x(x, y, hi, lo); }
 
 template <int D>
 __global__ void __launch_bounds__(256)

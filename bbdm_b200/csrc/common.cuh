@@ -58,15 +58,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+// two floats -> packed (hi, lo) bf16x2 words with ONE cvt.rn.bf16x2.f32 per plane (the scalar
+// conversions run on the quarter-rate XU pipe and were the attention kernel's top stall)
+__device__ __forceinline__ void split2x(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);          // .x = a (low half), .y = b
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // split 4 floats -> two uint2 (4 bf16 each)
 __device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
-  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-  split_bf16(v.x, h0, l0);
-  split_bf16(v.y, h1, l1);
-  split_bf16(v.z, h2, l2);
-  split_bf16(v.w, h3, l3);
-  hi = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-  lo = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+  split2x(v.x, v.y, hi.x, lo.x);
+  split2x(v.z, v.w, hi.y, lo.y);
 }
 
 template <typename T>
