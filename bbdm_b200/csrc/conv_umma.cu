@@ -22,12 +22,13 @@
 //   * Every mbarrier wait has a clock-based watchdog: on expiry a device fault word is set and
 //     the CTA drains without deadlocking the GPU (bbdm_check_device_fault reports it).
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace bbdm {
 
 constexpr int UM_BM = 128;       // pixels per tile (UMMA M)
-constexpr int UM_BK = 64;        // bf16 per K block = 128 B rows (SWIZZLE_128B)
-constexpr uint32_t UM_A_BYTES = UM_BM * UM_BK * 2;  // 16 KiB per plane per stage
+// K block = BK bf16 input channels of one tap: 64 (128-byte rows, SWIZZLE_128B, default) or 32
+// (64-byte rows, SWIZZLE_64B: half-size stages, 4-deep TMA ring for the 256-wide tiles).
 
 // Column sums over the 32 lanes (rows) of a warp for 32 per-lane values: reduce-scatter
 // butterfly, 31 shuffles; afterwards lane l holds the total of column l in v[0].
@@ -47,9 +48,9 @@ __device__ __forceinline__ void warp_colsum32(float* v, int lane) {
 struct ConvParams {
   int B, H, W, Cout;
   int TW, TH, TB, tiles_w, tiles_h, tiles_b, n_tiles;
-  int kb_per_tap;   // Cin / 64
+  int kb_per_tap;   // Cin / BK
   int K1;           // taps * Cin/64
-  int K2;           // Cin2 / 64
+  int K2;           // Cin2 / BK
   int taps;
   int up2;           // 1: fused nearest-2x upsample (4 output phases x 2x2 taps on the low-res input)
   int passes;
@@ -62,11 +63,12 @@ struct ConvParams {
   unsigned long long* fault;
 };
 
-template <int BN>
+template <int BN, int BK = 64>
 struct UmmaCfg {
-  static constexpr uint32_t W_BYTES = BN * UM_BK * 2;
-  static constexpr uint32_t STAGE3 = 2 * UM_A_BYTES + 2 * W_BYTES;  // hi+lo planes
-  static constexpr uint32_t STAGE1 = UM_A_BYTES + W_BYTES;
+  static constexpr uint32_t A_BYTES = UM_BM * BK * 2;     // per plane per stage
+  static constexpr uint32_t W_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE3 = 2 * A_BYTES + 2 * W_BYTES;  // hi+lo planes
+  static constexpr uint32_t STAGE1 = A_BYTES + W_BYTES;
   static constexpr uint32_t SMEM_BUDGET = 200 * 1024;
   static constexpr int STAGES3 = (SMEM_BUDGET / STAGE3) > 6 ? 6 : (SMEM_BUDGET / STAGE3);
   static constexpr int STAGES1 = (SMEM_BUDGET / STAGE1) > 8 ? 8 : (SMEM_BUDGET / STAGE1);
@@ -78,18 +80,32 @@ struct UmmaCfg {
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
 
-template <int BN, int PASSES>
+// shared-memory matrix descriptor for a K-major tile whose rows are BK bf16 wide
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
+  if (BK == 64) return make_sw128_desc(saddr);
+  // SWIZZLE_64B: 64-byte rows, 8-row groups 512 B apart, layout type 4
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+
+template <int BN, int PASSES, int BK>
 __global__ void __launch_bounds__(UmmaCfg<BN>::THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                  const __grid_constant__ CUtensorMap map_a2_hi, const __grid_constant__ CUtensorMap map_a2_lo,
                  const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
                  const ConvParams p) {
-  using Cfg = UmmaCfg<BN>;
+  using Cfg = UmmaCfg<BN, BK>;
   constexpr int STAGES = PASSES == 3 ? Cfg::STAGES3 : Cfg::STAGES1;
   constexpr uint32_t STAGE_BYTES = PASSES == 3 ? Cfg::STAGE3 : Cfg::STAGE1;
-  constexpr uint32_t OFF_ALO = UM_A_BYTES;
-  constexpr uint32_t OFF_WHI = PASSES == 3 ? 2 * UM_A_BYTES : UM_A_BYTES;
+  constexpr uint32_t OFF_ALO = Cfg::A_BYTES;
+  constexpr uint32_t OFF_WHI = PASSES == 3 ? 2 * Cfg::A_BYTES : Cfg::A_BYTES;
   constexpr uint32_t OFF_WLO = OFF_WHI + Cfg::W_BYTES;
   static_assert(STAGES >= 2, "need at least a double buffer");
 
@@ -155,16 +171,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               dx = (phase & 1) ? c : c - 1;
               wtap = phase * 4 + tap;
             } else if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-            tma_load_4d(sbase, &map_a_hi, full, cb * UM_BK, w0 + dx, h0 + dy, b0);
-            if (PASSES == 3) tma_load_4d(sbase + OFF_ALO, &map_a_lo, full, cb * UM_BK, w0 + dx, h0 + dy, b0);
-            tma_load_3d(sbase + OFF_WHI, &map_w_hi, full, cb * UM_BK, n0, wtap);
-            if (PASSES == 3) tma_load_3d(sbase + OFF_WLO, &map_w_lo, full, cb * UM_BK, n0, wtap);
+            tma_load_4d(sbase, &map_a_hi, full, cb * BK, w0 + dx, h0 + dy, b0);
+            if (PASSES == 3) tma_load_4d(sbase + OFF_ALO, &map_a_lo, full, cb * BK, w0 + dx, h0 + dy, b0);
+            tma_load_3d(sbase + OFF_WHI, &map_w_hi, full, cb * BK, n0, wtap);
+            if (PASSES == 3) tma_load_3d(sbase + OFF_WLO, &map_w_lo, full, cb * BK, n0, wtap);
           } else {
             const int cb = kb - p.K1;
-            tma_load_4d(sbase, &map_a2_hi, full, cb * UM_BK, w0, h0, b0);
-            if (PASSES == 3) tma_load_4d(sbase + OFF_ALO, &map_a2_lo, full, cb * UM_BK, w0, h0, b0);
-            tma_load_3d(sbase + OFF_WHI, &map_w2_hi, full, cb * UM_BK, n0, 0);
-            if (PASSES == 3) tma_load_3d(sbase + OFF_WLO, &map_w2_lo, full, cb * UM_BK, n0, 0);
+            tma_load_4d(sbase, &map_a2_hi, full, cb * BK, w0, h0, b0);
+            if (PASSES == 3) tma_load_4d(sbase + OFF_ALO, &map_a2_lo, full, cb * BK, w0, h0, b0);
+            tma_load_3d(sbase + OFF_WHI, &map_w2_hi, full, cb * BK, n0, 0);
+            if (PASSES == 3) tma_load_3d(sbase + OFF_WLO, &map_w2_lo, full, cb * BK, n0, 0);
           }
           if (++stage == STAGES) { stage = 0; phase_bit ^= 1; }
         }
@@ -191,12 +207,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             mbar_wait(bar_full + 8 * stage, phase, abort_flag, p.fault, 0xF0000000ull | (unsigned)kb);
             tc_fence_after();
             const uint32_t sbase = tiles_base + stage * STAGE_BYTES;
-            const uint64_t da_hi = make_sw128_desc(sbase);
-            const uint64_t da_lo = make_sw128_desc(sbase + OFF_ALO);
-            const uint64_t db_hi = make_sw128_desc(sbase + OFF_WHI);
-            const uint64_t db_lo = make_sw128_desc(sbase + OFF_WLO);
+            const uint64_t da_hi = make_kmajor_desc<BK>(sbase);
+            const uint64_t da_lo = make_kmajor_desc<BK>(sbase + OFF_ALO);
+            const uint64_t db_hi = make_kmajor_desc<BK>(sbase + OFF_WHI);
+            const uint64_t db_lo = make_kmajor_desc<BK>(sbase + OFF_WLO);
 #pragma unroll
-            for (int k = 0; k < UM_BK / 16; ++k) {
+            for (int k = 0; k < BK / 16; ++k) {
               const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 B per UMMA_K inside the swizzle atom
               const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;   // a chunk starts from zero
               if (PASSES == 3) {
@@ -360,15 +376,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 
 // ------------------------------------------------------------------------------- host side
 // bf16 NHWC activation [B,H,W,C] -> 4-D map (C, W, H, B), box (64, TW, TH, TB), SWIZZLE_128B
-static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int TW, int TH, int TB) {
+static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int TW, int TH, int TB, int BK) {
   EncodeTiledFn enc = get_encode();
   BBDM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)UM_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   BBDM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: %d (B=%d H=%d W=%d C=%d box=%dx%dx%d)",
                (int)r, B, H, W, C, TW, TH, TB);
@@ -376,15 +392,15 @@ static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, in
 }
 
 // bf16 weights [taps][Cout][Cin] -> 3-D map (Cin, Cout, taps), box (64, BN, 1)
-static int make_w_map(CUtensorMap* m, const void* ptr, int taps, int Cout, int Cin, int BN) {
+static int make_w_map(CUtensorMap* m, const void* ptr, int taps, int Cout, int Cin, int BN, int BK) {
   EncodeTiledFn enc = get_encode();
   BBDM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
   cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
-  cuuint32_t box[3] = {(cuuint32_t)UM_BK, (cuuint32_t)BN, 1};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   BBDM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed: %d (taps=%d Cout=%d Cin=%d BN=%d)", (int)r,
                taps, Cout, Cin, BN);
@@ -394,18 +410,18 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int taps, int Cout, int C
 static int pow2_floor(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
 static int pow2_ceil(int x) { int p = 1; while (p < x) p *= 2; return p; }
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, int BK>
 static int launch_conv(const CUtensorMap* maps, const ConvParams& p, int grid, cudaStream_t s) {
-  using Cfg = UmmaCfg<BN>;
+  using Cfg = UmmaCfg<BN, BK>;
   constexpr int STAGES = PASSES == 3 ? Cfg::STAGES3 : Cfg::STAGES1;
   constexpr uint32_t STAGE_BYTES = PASSES == 3 ? Cfg::STAGE3 : Cfg::STAGE1;
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
   static bool configured = false;
   if (!configured) {
-    BBDM_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BBDM_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<BN, PASSES, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  conv_umma_kernel<BN, PASSES><<<grid, Cfg::THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
+  conv_umma_kernel<BN, PASSES, BK><<<grid, Cfg::THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
                                                               maps[6], maps[7], p);
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
@@ -414,6 +430,13 @@ static int launch_conv(const CUtensorMap* maps, const ConvParams& p, int grid, c
 }  // namespace bbdm
 
 using namespace bbdm;
+
+// BBDM_CONV_BK=32 selects the 32-channel K block for the 256-wide tiles (A/B measurements)
+static int conv_bk_override() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BBDM_CONV_BK"); v = e ? atoi(e) : 0; }
+  return v;
+}
 
 static void tile_geometry(int H, int W, int* TW, int* TH, int* TB) {
   *TW = pow2_floor(W) < 16 ? pow2_floor(W) : 16;
@@ -458,13 +481,18 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   p.tiles_h = (a->H + p.TH - 1) / p.TH;
   p.tiles_b = (a->B + p.TB - 1) / p.TB;
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
-  p.kb_per_tap = a->Cin / 64;
+  const int BN = (a->Cout % 256 == 0) ? 256 : (a->Cout % 128 == 0 ? 128 : 64);
+  // BBDM_CONV_BK=32: 256-wide N tiles in split mode use 32-channel K blocks (4-stage TMA ring instead of
+  // 2).  Measured on B200 (round 1): the tensor pipe gets busier but the 1 kW power cap lowers the SM
+  // clock by the same factor (1522 -> 1335 MHz), identical step time -- so 64 stays the default.
+  const int BK = (BN == 256 && a->passes == 3 && conv_bk_override() == 32) ? 32 : 64;
+  p.kb_per_tap = a->Cin / BK;
   p.K1 = a->taps * p.kb_per_tap;
-  p.K2 = a->Cin2 / 64;
+  p.K2 = a->Cin2 / BK;
   p.taps = a->taps;
   p.up2 = a->upsample2x ? 1 : 0;
   p.passes = a->passes;
-  p.kb_per_chunk = a->passes == 3 ? 4 : 8;
+  p.kb_per_chunk = (a->passes == 3 ? 4 : 8) * (64 / BK);
   p.bias = a->bias; p.bias2 = a->Cin2 ? a->bias2 : nullptr;
   p.residual = a->residual; p.res_mode = a->res_mode;
   p.out = a->out; p.out_hi = (__nv_bfloat16*)a->out_hi; p.out_lo = (__nv_bfloat16*)a->out_lo;
@@ -477,19 +505,18 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
 
   BBDM_REQUIRE(p.stats == nullptr || (p.TB == 1 && p.out_nchw_c == 0),
                "conv_umma: stats_partial needs a tile inside one image (H*W >= 128) and NHWC output");
-  const int BN = (a->Cout % 256 == 0) ? 256 : (a->Cout % 128 == 0 ? 128 : 64);
   CUtensorMap maps[8];
   int rc;
-  if ((rc = make_act_map(&maps[0], a->a_hi, a->B, a->H, a->W, a->Cin, p.TW, p.TH, p.TB))) return rc;
-  if ((rc = make_act_map(&maps[1], a->passes == 3 ? a->a_lo : a->a_hi, a->B, a->H, a->W, a->Cin, p.TW, p.TH, p.TB))) return rc;
+  if ((rc = make_act_map(&maps[0], a->a_hi, a->B, a->H, a->W, a->Cin, p.TW, p.TH, p.TB, BK))) return rc;
+  if ((rc = make_act_map(&maps[1], a->passes == 3 ? a->a_lo : a->a_hi, a->B, a->H, a->W, a->Cin, p.TW, p.TH, p.TB, BK))) return rc;
   const int wtaps = a->upsample2x ? 16 : a->taps;
-  if ((rc = make_w_map(&maps[2], a->w_hi, wtaps, a->Cout, a->Cin, BN))) return rc;
-  if ((rc = make_w_map(&maps[3], a->passes == 3 ? a->w_lo : a->w_hi, wtaps, a->Cout, a->Cin, BN))) return rc;
+  if ((rc = make_w_map(&maps[2], a->w_hi, wtaps, a->Cout, a->Cin, BN, BK))) return rc;
+  if ((rc = make_w_map(&maps[3], a->passes == 3 ? a->w_lo : a->w_hi, wtaps, a->Cout, a->Cin, BN, BK))) return rc;
   if (a->Cin2) {
-    if ((rc = make_act_map(&maps[4], a->a2_hi, a->B, a->H, a->W, a->Cin2, p.TW, p.TH, p.TB))) return rc;
-    if ((rc = make_act_map(&maps[5], a->passes == 3 ? a->a2_lo : a->a2_hi, a->B, a->H, a->W, a->Cin2, p.TW, p.TH, p.TB))) return rc;
-    if ((rc = make_w_map(&maps[6], a->w2_hi, 1, a->Cout, a->Cin2, BN))) return rc;
-    if ((rc = make_w_map(&maps[7], a->passes == 3 ? a->w2_lo : a->w2_hi, 1, a->Cout, a->Cin2, BN))) return rc;
+    if ((rc = make_act_map(&maps[4], a->a2_hi, a->B, a->H, a->W, a->Cin2, p.TW, p.TH, p.TB, BK))) return rc;
+    if ((rc = make_act_map(&maps[5], a->passes == 3 ? a->a2_lo : a->a2_hi, a->B, a->H, a->W, a->Cin2, p.TW, p.TH, p.TB, BK))) return rc;
+    if ((rc = make_w_map(&maps[6], a->w2_hi, 1, a->Cout, a->Cin2, BN, BK))) return rc;
+    if ((rc = make_w_map(&maps[7], a->passes == 3 ? a->w2_lo : a->w2_hi, 1, a->Cout, a->Cin2, BN, BK))) return rc;
   } else {
     maps[4] = maps[0]; maps[5] = maps[1]; maps[6] = maps[2]; maps[7] = maps[3];
   }
@@ -498,7 +525,8 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   const int grid = (int)(total < num_sms() ? total : num_sms());
   cudaStream_t s = (cudaStream_t)stream;
 #define BBDM_UL(N)                                                        \
-  (a->passes == 3 ? launch_conv<N, 3>(maps, p, grid, s) : launch_conv<N, 1>(maps, p, grid, s))
+  (a->passes == 3 ? launch_conv<N, 3, 64>(maps, p, grid, s) : launch_conv<N, 1, 64>(maps, p, grid, s))
+  if (BN == 256 && BK == 32) return launch_conv<256, 3, 32>(maps, p, grid, s);
   if (BN == 256) return BBDM_UL(256);
   if (BN == 128) return BBDM_UL(128);
   return BBDM_UL(64);

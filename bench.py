@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=list(CONFIGS))
     ap.add_argument("--precision", default="split3", choices=["split3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-convs", default=None, help="write per-conv-launch shape/time/TFLOPs (profiled step) to this file")
     ap.add_argument("--graph", action="store_true", help="also time CUDA-graph replays of the captured sampling step")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
@@ -258,7 +259,8 @@ def main():
                 flops = 2.0 * kw["B"] * 4 * kw["H"] * kw["W"] * kw["Cout"] * 9 * kw["Cin"]
             else:
                 flops = 2.0 * kw["B"] * kw["H"] * kw["W"] * kw["Cout"] * (kw["taps"] * kw["Cin"] + kw.get("Cin2", 0))
-            ProfilingBackend.events.append((e0, e1, flops))
+            ProfilingBackend.events.append((e0, e1, flops, {k: kw[k] for k in ("B", "H", "W", "Cin", "Cout", "taps")} |
+                                            {"Cin2": kw.get("Cin2", 0), "up2": bool(kw.get("upsample2x")), "res": kw.get("res_mode", 0)}))
 
     BridgeOps.backend_factory = staticmethod(lambda: ProfilingBackend())
     net = BrownianBridgeModel(namespace(cfg["unet"], cfg["sample_step"])).eval()
@@ -356,8 +358,13 @@ def main():
     x2, _ = net.p_sample(x, y, ctx_of(y), 20)
     torch.cuda.synchronize()
     ProfilingBackend.record = False
-    conv_ms = sum(a.elapsed_time(b) for a, b, _ in ProfilingBackend.events)
-    conv_flops = sum(f for _, _, f in ProfilingBackend.events)
+    conv_ms = sum(e[0].elapsed_time(e[1]) for e in ProfilingBackend.events)
+    conv_flops = sum(e[2] for e in ProfilingBackend.events)
+    if args.dump_convs and rank == 0:
+        with open(args.dump_convs, "w") as f:
+            for e0_, e1_, fl, shp in ProfilingBackend.events:
+                ms_ = e0_.elapsed_time(e1_)
+                f.write(json.dumps({**shp, "ms": ms_, "algo_tflops": fl / ms_ / 1e9}) + "\n")
     n_conv = len(ProfilingBackend.events)
     peaks, peak_src = load_peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
