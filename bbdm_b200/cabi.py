@@ -28,6 +28,7 @@ SYMBOLS = [
     "bbdm_pack_weight_split", "bbdm_pack_weight_split_padded", "bbdm_pack_weight_split_taps",
     "bbdm_pack_weight_f32", "bbdm_conv_umma", "bbdm_conv_direct",
     "bbdm_attention", "bbdm_attention_split", "bbdm_attention_tc", "bbdm_conv_umma_geometry", "bbdm_gn_finalize_partials",
+    "bbdm_split_grad", "bbdm_conv_wgrad_workspace", "bbdm_conv_wgrad",
 ]
 
 
@@ -101,6 +102,9 @@ def load():
     lib.bbdm_attention.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp]
     lib.bbdm_conv_umma_geometry.argtypes = [i, i, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     lib.bbdm_gn_finalize_partials.argtypes = [vp, i, i, vp, i, i, i, i, i, f, vp, vp, vp]
+    lib.bbdm_split_grad.argtypes = [vp, i64, i, vp, vp, vp, vp, vp, vp, vp]
+    lib.bbdm_conv_wgrad_workspace.argtypes = [i, i, i, i, i, i, C.POINTER(i), C.POINTER(i64)]
+    lib.bbdm_conv_wgrad.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, vp, vp, vp]
     lib.bbdm_attention_split.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp]
     lib.bbdm_attention_tc.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp]
     for s in SYMBOLS:
@@ -265,6 +269,23 @@ class CudaBackend:
         check(self.lib.bbdm_gn_finalize_partials(ptr(_req(part1)), c1, rows1, ptr(part2), c2, rows2, B, hw, groups,
                                                  eps, ptr(_req(mean)), ptr(_req(rstd)), stream()))
         LAUNCHES["n"] += 1
+
+    # -- training gradients -----------------------------------------------------------------------
+    def split_grad(self, src, hi, lo, hi_t, lo_t, colsum=None, workspace=None):
+        P, Cc = src.numel() // src.shape[-1], src.shape[-1]
+        check(self.lib.bbdm_split_grad(ptr(_req(src)), P, Cc, ptr(hi), ptr(lo), ptr(hi_t), ptr(lo_t), ptr(colsum),
+                                       ptr(workspace), stream()))
+        LAUNCHES["n"] += 1 + (colsum is not None)
+
+    def wgrad_workspace(self, B, H, W, Cin, Cout, taps):
+        sp, fl = C.c_int(0), C.c_int64(0)
+        check(self.lib.bbdm_conv_wgrad_workspace(B, H, W, Cin, Cout, taps, C.byref(sp), C.byref(fl)))
+        return sp.value, fl.value
+
+    def conv_wgrad(self, g_hi_t, g_lo_t, a_hi, a_lo, B, H, W, Cin, Cout, taps, dw, workspace):
+        check(self.lib.bbdm_conv_wgrad(ptr(g_hi_t), ptr(g_lo_t), ptr(a_hi), ptr(a_lo), B, H, W, Cin, Cout, taps,
+                                       ptr(_req(dw)), ptr(_req(workspace)), stream()))
+        LAUNCHES["n"] += 2
 
     def conv_direct(self, src, w_packed, bias, residual, out, Cout, k, stride=1):
         B, H, W, Cin = src.shape

@@ -24,6 +24,12 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .train import conv2d as _conv2d
+
+# training path: ResBlock convolutions on the tcgen05 fwd / dgrad / wgrad kernels (bbdm_b200/train.py);
+# set False to run the whole training graph on stock PyTorch kernels
+NATIVE_TRAIN_CONV = True
+
 
 class GroupNorm32(nn.GroupNorm):
     """GroupNorm(32, C), eps 1e-5, computed in fp32 (reference util.py:199-216)."""
@@ -125,15 +131,18 @@ class ResBlock(TimestepBlock):
             x = F.interpolate(x, scale_factor=2, mode="nearest")
         elif self.down:
             h, x = F.avg_pool2d(h, 2), F.avg_pool2d(x, 2)
-        h = self.in_layers[2](h)
+        h = _conv2d(self.in_layers[2], h, NATIVE_TRAIN_CONV)
         e = self.emb_layers(emb).type(h.dtype)[:, :, None, None]
         if self.use_scale_shift_norm:
             scale, shift = torch.chunk(e, 2, dim=1)
             h = self.out_layers[0](h) * (1 + scale) + shift
-            h = self.out_layers[1:](h)
         else:
-            h = self.out_layers(h + e)
-        return self.skip_connection(x) + h
+            h = self.out_layers[0](h + e)
+        h = self.out_layers[2](self.out_layers[1](h))            # SiLU, Dropout
+        h = _conv2d(self.out_layers[3], h, NATIVE_TRAIN_CONV)
+        if isinstance(self.skip_connection, nn.Conv2d):
+            return _conv2d(self.skip_connection, x, NATIVE_TRAIN_CONV) + h
+        return x + h
 
 
 class AttentionBlock(nn.Module):

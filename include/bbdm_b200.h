@@ -233,6 +233,34 @@ int bbdm_conv_direct(const float* src, const float* w_packed, const float* bias,
                      int k, int stride, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training: gradients of the tensor-core convolution
+ *   data gradient   dX = conv(dY, W^T flipped)  -> bbdm_conv_umma with re-packed weights
+ *   weight gradient dW                          -> bbdm_conv_wgrad (below)
+ * Replaces the autograd of nn.Conv2d in ResBlock (openaimodel.py:207,233,244) during
+ * loss.backward() (runners/BaseRunner.py:412).
+ * ------------------------------------------------------------------------------------------ */
+
+/* fp32 NHWC gradient src [P][C] (P = B*H*W) -> split-bf16 planes in both orientations
+ *   hi/lo     [P][C]  (may be NULL)  : A operand of the data-gradient conv
+ *   hi_t/lo_t [C][P]                 : A operand (K = pixels) of the weight-gradient GEMM
+ * and, if colsum != NULL, colsum[c] = sum_p src[p][c] (the bias gradient; deterministic).
+ * workspace: ceil(P/64)*C floats (only needed with colsum). */
+int bbdm_split_grad(const float* src, int64_t P, int C, void* hi, void* lo, void* hi_t, void* lo_t,
+                    float* colsum, float* workspace, void* stream);
+
+/* split-K factor and workspace size (floats) bbdm_conv_wgrad needs for this problem. */
+int bbdm_conv_wgrad_workspace(int B, int H, int W, int Cin, int Cout, int taps, int* splits,
+                              int64_t* floats);
+
+/* dW[co][ci][ky][kx] (OIHW fp32, overwritten) = sum_p dY[p][co] * A[p + tap][ci] on tcgen05:
+ * g_hi_t/g_lo_t = dY^T planes [Cout][P] from bbdm_split_grad, a_hi/a_lo = the forward conv's
+ * operand planes [B,H,W,Cin].  M = Cout, N = Cin, K = pixels; split-bf16 x3; split-K partials
+ * reduced in a fixed order.  Requirements: Cin, Cout % 64 == 0, taps in {1, 9}, B*H*W % 64 == 0. */
+int bbdm_conv_wgrad(const void* g_hi_t, const void* g_lo_t, const void* a_hi, const void* a_lo,
+                    int B, int H, int W, int Cin, int Cout, int taps, float* dw, float* workspace,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Attention core
  * ------------------------------------------------------------------------------------------ */
 

@@ -1,0 +1,126 @@
+"""-m gpu: the training path's native pieces -- gradient operand split, tcgen05 weight-gradient
+GEMM, data gradient through the forward conv kernel, the autograd Function, and one full
+training step against the stock-PyTorch graph."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _recipe import UNET_CONFIGS, bb_namespace, fill_state_dict, rel_dev
+from oracle import bbdm_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def be():
+    from bbdm_b200 import cabi
+    b = cabi.CudaBackend()
+    yield b
+    b.check_fault()
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (scale * torch.randn(shape, generator=g)).float()
+
+
+@pytest.mark.parametrize("P,C", [(256, 64), (1000, 96), (4096, 128), (64, 200)])
+def test_split_grad(be, P, C):
+    x = rnd((P, C), 1)
+    hi, lo = torch.empty((P, C), dtype=torch.bfloat16, device=DEV), torch.empty((P, C), dtype=torch.bfloat16, device=DEV)
+    ht, lt = torch.empty((C, P), dtype=torch.bfloat16, device=DEV), torch.empty((C, P), dtype=torch.bfloat16, device=DEV)
+    cs = torch.empty((C,), device=DEV)
+    ws = torch.empty(((P + 63) // 64) * C, device=DEV)
+    be.split_grad(x.to(DEV), hi, lo, ht, lt, cs, ws)
+    h, l = O.bf16_split(x)
+    assert torch.equal(hi.float().cpu(), h) and torch.equal(lo.float().cpu(), l)
+    assert torch.equal(ht.float().cpu(), h.T.contiguous()) and torch.equal(lt.float().cpu(), l.T.contiguous())
+    assert rel_dev(cs, x.double().sum(0)) < 1e-6
+
+
+WG_CASES = [
+    # B, H, W, Cin, Cout, k
+    (2, 8, 8, 64, 64, 3),        # BN = 64 (single MN atom), 64-pixel box = one image
+    (1, 16, 16, 128, 128, 3),    # BN = 128: two MN atoms (LBO)
+    (2, 16, 16, 256, 128, 3),    # BN = 256: four MN atoms, 8 promotion warps
+    (2, 64, 64, 64, 192, 3),     # box = one row of 64; Cout tile partially out of range
+    (4, 4, 4, 128, 64, 3),       # box spans 4 images
+    (2, 16, 16, 128, 256, 1),    # 1x1
+    (1, 32, 32, 512, 512, 3),    # deeper K split
+]
+
+
+@pytest.mark.parametrize("case", WG_CASES)
+def test_conv_wgrad(be, case):
+    B, H, W, Cin, Cout, k = case
+    a = rnd((B, H, W, Cin), 2)
+    g = rnd((B, H, W, Cout), 3, 0.1)
+    P = B * H * W
+    a_hi, a_lo = (t.to(torch.bfloat16).to(DEV) for t in O.bf16_split(a))
+    ht, lt = torch.empty((Cout, P), dtype=torch.bfloat16, device=DEV), torch.empty((Cout, P), dtype=torch.bfloat16, device=DEV)
+    be.split_grad(g.reshape(P, Cout).to(DEV), None, None, ht, lt)
+    _, fl = be.wgrad_workspace(B, H, W, Cin, Cout, k * k)
+    ws = torch.empty(fl, device=DEV)
+    dw = torch.full((Cout, Cin, k, k), float("nan"), device=DEV)
+    be.conv_wgrad(ht, lt, a_hi, a_lo, B, H, W, Cin, Cout, k * k, dw, ws)
+    torch.cuda.synchronize()
+    be.check_fault()
+    # exact gradient for the values the planes carry
+    av = sum(O.bf16_split(a)).double().permute(0, 3, 1, 2).requires_grad_(False)
+    gv = sum(O.bf16_split(g)).double().permute(0, 3, 1, 2)
+    w = torch.zeros((Cout, Cin, k, k), dtype=torch.float64, requires_grad=True)
+    F.conv2d(av, w, padding=k // 2).backward(gv)
+    assert not torch.isnan(dw).any()
+    assert rel_dev(dw, w.grad) < 2e-5, rel_dev(dw, w.grad)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,bias", [(2, 16, 16, 64, 128, 3, True), (1, 32, 32, 128, 64, 3, False),
+                                                    (2, 8, 8, 256, 256, 1, True)])
+def test_conv2d_function_gradients(B, H, W, Cin, Cout, k, bias):
+    from bbdm_b200.train import Conv2dFn
+    x = rnd((B, Cin, H, W), 4).to(DEV).requires_grad_(True)
+    w = rnd((Cout, Cin, k, k), 5, 0.05).to(DEV).requires_grad_(True)
+    b = rnd((Cout,), 6, 0.1).to(DEV).requires_grad_(True) if bias else None
+    gy = rnd((B, Cout, H, W), 7, 0.2).to(DEV)
+    y = Conv2dFn.apply(x, w, b)
+    y.backward(gy)
+    xd, wd = x.detach().double().cpu().requires_grad_(True), w.detach().double().cpu().requires_grad_(True)
+    bd = None if b is None else b.detach().double().cpu().requires_grad_(True)
+    yd = F.conv2d(xd, wd, bd, padding=k // 2)
+    yd.backward(gy.double().cpu())
+    assert rel_dev(y, yd) < 3e-5
+    assert rel_dev(x.grad, xd.grad) < 3e-5
+    assert rel_dev(w.grad, wd.grad) < 3e-5
+    if bias:
+        assert rel_dev(b.grad, bd.grad) < 1e-5
+
+
+def test_training_step_native_convs_match_library_graph():
+    """loss and parameter gradients of one training step: tensor-core conv path vs stock PyTorch."""
+    import bbdm_b200.unet as U
+    from model.BrownianBridge.BrownianBridgeModel import BrownianBridgeModel
+    g = {k: torch.from_numpy(v) if v.ndim else v for k, v in np.load(os.path.join(os.path.dirname(__file__), "golden", "mid_pixel.npz")).items()}
+    net = BrownianBridgeModel(bb_namespace(UNET_CONFIGS["mid_pixel"])).train()
+    shapes = {k: tuple(v.shape) for k, v in net.denoise_fn.state_dict().items()}
+    net.denoise_fn.load_state_dict(fill_state_dict(shapes, seed=1234))
+    net = net.cuda()
+    x, y, t, nz = (g[k].cuda() for k in ("x", "y", "t", "q_noise"))
+    res = {}
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for native in (True, False):
+        U.NATIVE_TRAIN_CONV = native
+        net.zero_grad(set_to_none=True)
+        loss, _ = net.p_losses(x, y, y, t, nz)
+        loss.backward()
+        res[native] = (float(loss), {n: p.grad.detach().clone() for n, p in net.denoise_fn.named_parameters()})
+    U.NATIVE_TRAIN_CONV = True
+    assert abs(res[True][0] - float(g["loss"])) < 2e-4 * abs(float(g["loss"]))
+    assert abs(res[True][0] - res[False][0]) < 1e-4 * abs(res[False][0])
+    worst = max(rel_dev(res[True][1][n], res[False][1][n]) for n in res[False][1])
+    print(f"\n[train] loss native {res[True][0]:.6f} library {res[False][0]:.6f}; worst grad rel dev {worst:.3e}")
+    assert worst < 2e-3
