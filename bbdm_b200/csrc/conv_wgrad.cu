@@ -277,12 +277,23 @@ split_grad_kernel(const float* __restrict__ src, int64_t P, int C, __nv_bfloat16
   }
 }
 
-__global__ void colsum_reduce_kernel(const float* __restrict__ part, int64_t nblk, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// one CTA per 32 channels: 8 row-lanes x 32 channels, fixed-order fp64 tree => deterministic
+__global__ void __launch_bounds__(256)
+colsum_reduce_kernel(const float* __restrict__ part, int64_t nblk, int C, float* __restrict__ out) {
+  __shared__ double sm[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   double s = 0.0;
-  for (int64_t b = 0; b < nblk; ++b) s += (double)part[b * C + c];
-  out[c] = (float)s;
+  if (c < C)
+    for (int64_t b = ry; b < nblk; b += 8) s += (double)part[b * C + c];
+  sm[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    double t = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += sm[r][cx];
+    out[c] = (float)t;
+  }
 }
 
 static int make_gt_map(CUtensorMap* m, const void* ptr, int Cout, int64_t P) {
@@ -347,7 +358,7 @@ int bbdm_split_grad(const float* src, int64_t P, int C, void* hi, void* lo, void
                                          (__nv_bfloat16*)lo_t, colsum ? workspace : nullptr);
   BBDM_LAUNCH_CHECK();
   if (colsum) {
-    colsum_reduce_kernel<<<(C + 127) / 128, 128, 0, s>>>(workspace, nb, C, colsum);
+    colsum_reduce_kernel<<<(C + 31) / 32, 256, 0, s>>>(workspace, nb, C, colsum);
     BBDM_LAUNCH_CHECK();
   }
   return BBDM_OK;
