@@ -28,7 +28,7 @@ SYMBOLS = [
     "bbdm_pack_weight_split", "bbdm_pack_weight_split_padded", "bbdm_pack_weight_split_taps",
     "bbdm_pack_weight_f32", "bbdm_conv_umma", "bbdm_conv_direct",
     "bbdm_attention", "bbdm_attention_split", "bbdm_attention_tc", "bbdm_conv_umma_geometry", "bbdm_gn_finalize_partials",
-    "bbdm_split_grad", "bbdm_conv_wgrad_workspace", "bbdm_conv_wgrad",
+    "bbdm_split_grad", "bbdm_conv_wgrad_workspace", "bbdm_conv_wgrad", "bbdm_gn_bwd_reduce", "bbdm_gn_bwd_apply",
 ]
 
 
@@ -105,6 +105,8 @@ def load():
     lib.bbdm_split_grad.argtypes = [vp, i64, i, vp, vp, vp, vp, vp, vp, vp]
     lib.bbdm_conv_wgrad_workspace.argtypes = [i, i, i, i, i, i, C.POINTER(i), C.POINTER(i64)]
     lib.bbdm_conv_wgrad.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, vp, vp, vp]
+    lib.bbdm_gn_bwd_reduce.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp, vp, i64, i, vp, vp, vp]
+    lib.bbdm_gn_bwd_apply.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp, vp, i64, i, vp, vp, vp, vp]
     lib.bbdm_attention_split.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp]
     lib.bbdm_attention_tc.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp]
     for s in SYMBOLS:
@@ -286,6 +288,20 @@ class CudaBackend:
         check(self.lib.bbdm_conv_wgrad(ptr(g_hi_t), ptr(g_lo_t), ptr(a_hi), ptr(a_lo), B, H, W, Cin, Cout, taps,
                                        ptr(_req(dw)), ptr(_req(workspace)), stream()))
         LAUNCHES["n"] += 2
+
+    def gn_bwd_reduce(self, x, da, groups, mean, rstd, gamma, beta, fscale, fshift, fstride, silu, a12, ws):
+        B, H, W, Cc = x.shape
+        check(self.lib.bbdm_gn_bwd_reduce(ptr(_req(x)), ptr(_req(da)), B, H, W, Cc, groups, ptr(mean), ptr(rstd),
+                                          ptr(gamma), ptr(beta), ptr(fscale), ptr(fshift), fstride, int(silu),
+                                          ptr(_req(a12)), ptr(_req(ws)), stream()))
+        LAUNCHES["n"] += 2
+
+    def gn_bwd_apply(self, x, da, groups, mean, rstd, gamma, beta, fscale, fshift, fstride, silu, s1, s2, dx):
+        B, H, W, Cc = x.shape
+        check(self.lib.bbdm_gn_bwd_apply(ptr(_req(x)), ptr(_req(da)), B, H, W, Cc, groups, ptr(mean), ptr(rstd),
+                                         ptr(gamma), ptr(beta), ptr(fscale), ptr(fshift), fstride, int(silu),
+                                         ptr(_req(s1)), ptr(_req(s2)), ptr(_req(dx)), stream()))
+        LAUNCHES["n"] += 1
 
     def conv_direct(self, src, w_packed, bias, residual, out, Cout, k, stride=1):
         B, H, W, Cin = src.shape

@@ -80,43 +80,119 @@ class Conv2dFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        be = backend()
         a_hi, a_lo, weight = ctx.saved_tensors
+        dxn, dw, dbias = _conv_backward(backend(), ctx.shape, a_hi, a_lo, weight, dy, ctx.needs_input_grad[0],
+                                        ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2])
+        return (None if dxn is None else dxn.permute(0, 3, 1, 2)), dw, dbias
+
+
+def _conv_backward(be, ctx_shape, a_hi, a_lo, weight, dy, need_dx, need_dw, need_db):
+    """Shared by both Functions: (dA or dX as NHWC fp32, dW, dbias) of the tensor-core conv."""
+    B, H, W, Cin, Cout, k = ctx_shape
+    dev = dy.device
+    P = B * H * W
+    dyn = _nhwc(dy)
+    g_hi = g_lo = None
+    if need_dx:
+        g_hi = torch.empty((B, H, W, Cout), dtype=torch.bfloat16, device=dev)
+        g_lo = torch.empty_like(g_hi)
+    gt_hi = torch.empty((Cout, P), dtype=torch.bfloat16, device=dev)
+    gt_lo = torch.empty_like(gt_hi)
+    dbias = ws_b = None
+    if need_db:
+        dbias = torch.empty((Cout,), dtype=torch.float32, device=dev)
+        ws_b = torch.empty(((P + 63) // 64) * Cout, dtype=torch.float32, device=dev)
+    be.split_grad(dyn, g_hi, g_lo, gt_hi, gt_lo, dbias, ws_b)
+    dxn = None
+    if need_dx:
+        wd = weight.detach().flip(2, 3).transpose(0, 1).contiguous()          # [Cin, Cout, k, k]
+        wd_hi = torch.empty((k * k, Cin, Cout), dtype=torch.bfloat16, device=dev)
+        wd_lo = torch.empty_like(wd_hi)
+        be.pack_weight_split(wd, wd_hi, wd_lo)
+        dxn = torch.empty((B, H, W, Cin), dtype=torch.float32, device=dev)
+        be.conv_umma(B=B, H=H, W=W, Cin=Cout, Cout=Cin, taps=k * k, a_hi=g_hi, a_lo=g_lo, w_hi=wd_hi, w_lo=wd_lo,
+                     out=dxn, passes=3)
+    dw = None
+    if need_dw:
+        _, fl = be.wgrad_workspace(B, H, W, Cin, Cout, k * k)
+        ws = torch.empty((fl,), dtype=torch.float32, device=dev)
+        dw = torch.empty((Cout, Cin, k, k), dtype=torch.float32, device=dev)
+        be.conv_wgrad(gt_hi, gt_lo, a_hi, a_lo, B, H, W, Cin, Cout, k * k, dw, ws)
+    return dxn, dw, dbias
+
+
+class GNActConv2dFn(torch.autograd.Function):
+    """conv( silu( GroupNorm32(x) * (1 + scale) + shift ) ) fused: the forward is the sampling path's
+    stats + prep + tcgen05 conv; the backward adds the two-pass GroupNorm/SiLU/FiLM gradient kernels."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, scale, shift, weight, bias):
+        be = backend()
+        B, Cin, H, W = x.shape
+        Cout, _, k, _ = weight.shape
+        dev = x.device
+        xn = _nhwc(x.detach())
+        mean = torch.empty((B, 32), dtype=torch.float32, device=dev)
+        rstd = torch.empty_like(mean)
+        ws = torch.empty((B * 32 * cabi.GN_MAX_SLICES * 2,), dtype=torch.float64, device=dev)
+        be.gn_stats(xn, None, 32, 1e-5, mean, rstd, ws)
+        fs = fh = None
+        if scale is not None:
+            fs, fh = scale.detach().contiguous().float(), shift.detach().contiguous().float()
+        a_hi = torch.empty((B, H, W, Cin), dtype=torch.bfloat16, device=dev)
+        a_lo = torch.empty_like(a_hi)
+        be.prep(xn, None, groups=32, mean=mean, rstd=rstd, gamma=gamma.detach(), beta=beta.detach(), film_scale=fs,
+                film_shift=fh, film_stride=0 if fs is None else fs.shape[1], silu=True, act_hi=a_hi, act_lo=a_lo)
+        w_hi = torch.empty((k * k, Cout, Cin), dtype=torch.bfloat16, device=dev)
+        w_lo = torch.empty_like(w_hi)
+        be.pack_weight_split(weight.detach().contiguous(), w_hi, w_lo)
+        out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=dev)
+        be.conv_umma(B=B, H=H, W=W, Cin=Cin, Cout=Cout, taps=k * k, a_hi=a_hi, a_lo=a_lo, w_hi=w_hi, w_lo=w_lo,
+                     bias=None if bias is None else bias.detach(), out=out, passes=3)
+        ctx.save_for_backward(xn, mean, rstd, gamma, beta, fs, fh, a_hi, a_lo, weight)
+        ctx.has_bias = bias is not None
+        ctx.shape = (B, H, W, Cin, Cout, k)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        be = backend()
+        xn, mean, rstd, gamma, beta, fs, fh, a_hi, a_lo, weight = ctx.saved_tensors
         B, H, W, Cin, Cout, k = ctx.shape
         dev = dy.device
-        P = B * H * W
-        dyn = _nhwc(dy)
-        need_dx = ctx.needs_input_grad[0]
-        g_hi = g_lo = None
-        if need_dx:
-            g_hi = torch.empty((B, H, W, Cout), dtype=torch.bfloat16, device=dev)
-            g_lo = torch.empty_like(g_hi)
-        gt_hi = torch.empty((Cout, P), dtype=torch.bfloat16, device=dev)
-        gt_lo = torch.empty_like(gt_hi)
-        dbias = ws_b = None
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            dbias = torch.empty((Cout,), dtype=torch.float32, device=dev)
-            ws_b = torch.empty(((P + 63) // 64) * Cout, dtype=torch.float32, device=dev)
-        be.split_grad(dyn, g_hi, g_lo, gt_hi, gt_lo, dbias, ws_b)
+        da, dw, dbias = _conv_backward(be, ctx.shape, a_hi, a_lo, weight, dy, True, ctx.needs_input_grad[5],
+                                       ctx.has_bias and ctx.needs_input_grad[6])
+        g, b_ = gamma.detach(), beta.detach()
+        fstride = 0 if fs is None else fs.shape[1]
+        a12 = torch.empty((B, Cin, 2), dtype=torch.float32, device=dev)
+        ws = torch.empty((B * 64 * Cin * 2,), dtype=torch.float32, device=dev)
+        be.gn_bwd_reduce(xn, da, 32, mean, rstd, g, b_, fs, fh, fstride, True, a12, ws)
+        a1, a2 = a12[..., 0], a12[..., 1]                                  # [B, C]
+        f1 = (1.0 + fs) if fs is not None else torch.ones_like(a1)
+        dgamma = (f1 * a2).sum(0)
+        dbeta = (f1 * a1).sum(0)
+        dscale = dshift = None
+        if fs is not None:
+            dshift = a1
+            dscale = g * a2 + b_ * a1
+        gf = g * f1                                                       # [B, C]
+        s1 = (gf * a1).view(B, 32, Cin // 32).sum(2).contiguous()
+        s2 = (gf * a2).view(B, 32, Cin // 32).sum(2).contiguous()
+        dxn = torch.empty((B, H, W, Cin), dtype=torch.float32, device=dev)
+        be.gn_bwd_apply(xn, da, 32, mean, rstd, g, b_, fs, fh, fstride, True, s1, s2, dxn)
+        return dxn.permute(0, 3, 1, 2), dgamma, dbeta, dscale, dshift, dw, dbias
 
-        dx = None
-        if need_dx:
-            # data gradient = the same conv with the kernel flipped and Cin/Cout swapped
-            wd = weight.detach().flip(2, 3).transpose(0, 1).contiguous()          # [Cin, Cout, k, k]
-            wd_hi = torch.empty((k * k, Cin, Cout), dtype=torch.bfloat16, device=dev)
-            wd_lo = torch.empty_like(wd_hi)
-            be.pack_weight_split(wd, wd_hi, wd_lo)
-            dxn = torch.empty((B, H, W, Cin), dtype=torch.float32, device=dev)
-            be.conv_umma(B=B, H=H, W=W, Cin=Cout, Cout=Cin, taps=k * k, a_hi=g_hi, a_lo=g_lo, w_hi=wd_hi, w_lo=wd_lo,
-                         out=dxn, passes=3)
-            dx = dxn.permute(0, 3, 1, 2)
-        dw = None
-        if ctx.needs_input_grad[1]:
-            _, fl = be.wgrad_workspace(B, H, W, Cin, Cout, k * k)
-            ws = torch.empty((fl,), dtype=torch.float32, device=dev)
-            dw = torch.empty((Cout, Cin, k, k), dtype=torch.float32, device=dev)
-            be.conv_wgrad(gt_hi, gt_lo, a_hi, a_lo, B, H, W, Cin, Cout, k * k, dw, ws)
-        return dx, dw, dbias
+
+def gn_act_conv2d(norm, conv, x, scale=None, shift=None, enabled=True):
+    """conv(silu(norm(x) * (1 + scale) + shift)) -- fused tensor-core path when the shape qualifies."""
+    if enabled and native_ok(conv, x) and x.shape[1] % 32 == 0 and x.shape[1] <= 4096:
+        sc = None if scale is None else scale.reshape(scale.shape[0], -1)
+        sh = None if shift is None else shift.reshape(shift.shape[0], -1)
+        return GNActConv2dFn.apply(x, norm.weight, norm.bias, sc, sh, conv.weight, conv.bias)
+    h = norm(x)
+    if scale is not None:
+        h = h * (1 + scale) + shift
+    return conv2d(conv, torch.nn.functional.silu(h), enabled)
 
 
 def conv2d(conv: torch.nn.Conv2d, x: torch.Tensor, enabled: bool = True) -> torch.Tensor:

@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .train import conv2d as _conv2d
+from .train import conv2d as _conv2d, gn_act_conv2d as _gn_act_conv2d
 
 # training path: ResBlock convolutions on the tcgen05 fwd / dgrad / wgrad kernels (bbdm_b200/train.py);
 # set False to run the whole training graph on stock PyTorch kernels
@@ -125,23 +125,33 @@ class ResBlock(TimestepBlock):
             self.skip_connection = nn.Conv2d(channels, self.out_channels, 1)
 
     def forward(self, x, emb):
-        h = self.in_layers[1](self.in_layers[0](x))
-        if self.up:
-            h = F.interpolate(h, scale_factor=2, mode="nearest")
-            x = F.interpolate(x, scale_factor=2, mode="nearest")
-        elif self.down:
-            h, x = F.avg_pool2d(h, 2), F.avg_pool2d(x, 2)
-        h = _conv2d(self.in_layers[2], h, NATIVE_TRAIN_CONV)
-        e = self.emb_layers(emb).type(h.dtype)[:, :, None, None]
-        if self.use_scale_shift_norm:
-            scale, shift = torch.chunk(e, 2, dim=1)
-            h = self.out_layers[0](h) * (1 + scale) + shift
+        """Training / autograd graph.  On CUDA the GN+SiLU(+FiLM)+conv chains run as fused autograd
+        Functions over the tensor-core kernels (bbdm_b200/train.py) when shapes qualify."""
+        nat = NATIVE_TRAIN_CONV
+        if self.up or self.down:
+            h = self.in_layers[1](self.in_layers[0](x))
+            if self.up:
+                h = F.interpolate(h, scale_factor=2, mode="nearest")
+                x = F.interpolate(x, scale_factor=2, mode="nearest")
+            else:
+                h, x = F.avg_pool2d(h, 2), F.avg_pool2d(x, 2)
+            h = _conv2d(self.in_layers[2], h, nat)
         else:
-            h = self.out_layers[0](h + e)
-        h = self.out_layers[2](self.out_layers[1](h))            # SiLU, Dropout
-        h = _conv2d(self.out_layers[3], h, NATIVE_TRAIN_CONV)
+            h = _gn_act_conv2d(self.in_layers[0], self.in_layers[2], x, None, None, nat)
+        e = self.emb_layers(emb).type(h.dtype)[:, :, None, None]
+        if self.use_scale_shift_norm and self.dropout == 0:
+            scale, shift = torch.chunk(e, 2, dim=1)
+            h = _gn_act_conv2d(self.out_layers[0], self.out_layers[3], h, scale, shift, nat)
+        else:
+            if self.use_scale_shift_norm:
+                scale, shift = torch.chunk(e, 2, dim=1)
+                h = self.out_layers[0](h) * (1 + scale) + shift
+            else:
+                h = self.out_layers[0](h + e)
+            h = self.out_layers[2](self.out_layers[1](h))            # SiLU, Dropout
+            h = _conv2d(self.out_layers[3], h, nat)
         if isinstance(self.skip_connection, nn.Conv2d):
-            return _conv2d(self.skip_connection, x, NATIVE_TRAIN_CONV) + h
+            return _conv2d(self.skip_connection, x, nat) + h
         return x + h
 
 

@@ -260,6 +260,21 @@ int bbdm_conv_wgrad(const void* g_hi_t, const void* g_lo_t, const void* a_hi, co
                     int B, int H, int W, int Cin, int Cout, int taps, float* dw, float* workspace,
                     void* stream);
 
+/* Backward of the fused operand preparation  a = silu( (gamma*xh + beta) * (1+scale) + shift ),
+ * xh = (x-mean)*rstd  (training path; replaces the autograd of GroupNorm32 + SiLU + scale-shift,
+ * openaimodel.py:205-206,229-230,270-274).  Two HBM-bound passes over (x, dA):
+ *   bbdm_gn_bwd_reduce : a12[b][c] = (sum_p dz, sum_p dz*xh), dz = dA*silu'(z); workspace B*64*C*2 floats
+ *   bbdm_gn_bwd_apply  : dx = rstd*(dz*gamma*(1+scale) - (s1 + xh*s2)/n) with the per-(b,group) sums
+ *                        s1, s2 the host derives from a12 (as are dgamma, dbeta, dscale, dshift). */
+int bbdm_gn_bwd_reduce(const float* x, const float* da, int B, int H, int W, int C, int groups,
+                       const float* mean, const float* rstd, const float* gamma, const float* beta,
+                       const float* film_scale, const float* film_shift, int64_t film_stride, int silu,
+                       float* a12, float* workspace, void* stream);
+int bbdm_gn_bwd_apply(const float* x, const float* da, int B, int H, int W, int C, int groups,
+                      const float* mean, const float* rstd, const float* gamma, const float* beta,
+                      const float* film_scale, const float* film_shift, int64_t film_stride, int silu,
+                      const float* s1, const float* s2, float* dx, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Attention core
  * ------------------------------------------------------------------------------------------ */

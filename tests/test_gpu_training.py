@@ -124,3 +124,32 @@ def test_training_step_native_convs_match_library_graph():
     worst = max(rel_dev(res[True][1][n], res[False][1][n]) for n in res[False][1])
     print(f"\n[train] loss native {res[True][0]:.6f} library {res[False][0]:.6f}; worst grad rel dev {worst:.3e}")
     assert worst < 2e-3
+
+
+@pytest.mark.parametrize("B,H,W,C,Cout,film", [(2, 16, 16, 64, 128, True), (3, 8, 8, 128, 64, False), (2, 32, 32, 640, 128, True)])
+def test_gn_act_conv_function_gradients(B, H, W, C, Cout, film):
+    """conv(silu(GN(x)*(1+scale)+shift)) fused Function: outputs and ALL gradients vs an fp64 torch graph."""
+    from bbdm_b200.train import GNActConv2dFn
+    mk = lambda t: t.to(DEV).requires_grad_(True)
+    x = mk(rnd((B, C, H, W), 10) + 0.2)
+    gamma, beta = mk(1 + 0.1 * rnd((C,), 11)), mk(0.1 * rnd((C,), 12))
+    scale = mk(0.3 * rnd((B, C), 13)) if film else None
+    shift = mk(0.3 * rnd((B, C), 14)) if film else None
+    w, b = mk(rnd((Cout, C, 3, 3), 15, 0.05)), mk(rnd((Cout,), 16, 0.1))
+    gy = rnd((B, Cout, H, W), 17, 0.2).to(DEV)
+    y = GNActConv2dFn.apply(x, gamma, beta, scale, shift, w, b)
+    y.backward(gy)
+
+    d = lambda t: None if t is None else t.detach().double().cpu().requires_grad_(True)
+    xd, gd, bd, sd, hd, wd, bbd = d(x), d(gamma), d(beta), d(scale), d(shift), d(w), d(b)
+    h = F.group_norm(xd, 32, gd, bd, 1e-5)
+    if film:
+        h = h * (1 + sd[:, :, None, None]) + hd[:, :, None, None]
+    yd = F.conv2d(F.silu(h), wd, bbd, padding=1)
+    yd.backward(gy.double().cpu())
+    assert rel_dev(y, yd) < 3e-5
+    pairs = [("x", x, xd), ("gamma", gamma, gd), ("beta", beta, bd), ("w", w, wd), ("b", b, bbd)]
+    if film:
+        pairs += [("scale", scale, sd), ("shift", shift, hd)]
+    for name, a, r in pairs:
+        assert rel_dev(a.grad, r.grad) < 5e-5, (name, rel_dev(a.grad, r.grad))
