@@ -1,9 +1,9 @@
 // Flash-style multi-head attention core for AttentionBlock (openaimodel.py:350-413).
 //   out = softmax((q*s)(k*s)^T) v,  s = head_dim^-1/4, softmax in fp32, no T x T buffer.
 // Tensor-core products use split-bf16 operands (hi.hi + lo.hi + hi.lo, fp32 accumulate) so the
-// result is fp32-class accurate.  Round-1 implementation: mma.sync.m16n8k16 (legacy tensor
-// path, HMMA) -- attention is <= 1.7 % of the step FLOPs; a tcgen05/TMEM
-// version is listed under "next" in DESIGN.md.
+// result is fp32-class accurate.  mma.sync.m16n8k16 variant reading fp32 qkv: serves UNets whose
+// qkv conv runs on the fp32 direct kernel (unaligned channel counts).  The template UNets
+// (head_dim 64) use the warp-specialised tcgen05 kernel in attention_tc.cu.
 //
 // CTA = 4 warps x 16 query rows = 64 queries of one (batch, head); KV tiles of 64 keys.
 #include "common.cuh"

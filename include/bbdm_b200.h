@@ -178,7 +178,7 @@ enum { BBDM_RES_NONE = 0, BBDM_RES_SAME = 1, BBDM_RES_UP2 = 2, BBDM_RES_DOWN2 = 
  * TMA (4-D tiled maps, OOB zero fill = the conv padding), accumulate in TMEM (fp32).
  * passes = 3: A_hi.W_hi + A_lo.W_hi + A_hi.W_lo  (fp32-class accuracy, the parity mode)
  * passes = 1: A_hi.W_hi                           (plain bf16)
- * Requirements: Cin % 64 == 0, Cin2 % 64 == 0, Cout % 16 == 0, taps in {1, 9}.
+ * Requirements: Cin % 64 == 0, Cin2 % 64 == 0, Cout % 64 == 0, taps in {1, 9} (4 with upsample2x), W >= 4.
  * Replaces nn.Conv2d 3x3 / 1x1 in ResBlock (openaimodel.py:207,233,244), the qkv / proj_out
  * nn.Conv1d of AttentionBlock (:307,315) and the residual adds (:278,327). */
 typedef struct {

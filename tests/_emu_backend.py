@@ -7,16 +7,13 @@ import torch.nn.functional as F
 
 from oracle import bbdm_oracle as O
 
-RESAMPLE = {0: 0, 1: 1, 2: 2}
-
 
 class EmuBackend:
     name = "oracle-emulation (tests only)"
     requires_cuda = False
 
-    def __init__(self, split_emulation=False):
+    def __init__(self):
         self.calls = []
-        self.split = split_emulation   # True: emulate the split-bf16 rounding of the operands
 
     def empty(self, shape, dtype, device):
         # poison so that reading an unwritten / prematurely recycled buffer shows up as NaN
