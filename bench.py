@@ -153,7 +153,10 @@ def load_peaks():
 # CPU arm: the oracle port (pure torch CPU restatement of the reference algorithm) on the host
 # cores.  /root/reference is Python and does not exist on the GPU box, so kind = "port".
 # ------------------------------------------------------------------------------------------
-def cpu_step_time(cfg, sample_batch, n_steps, threads):
+def cpu_step_time(cfg, sample_batch, n_steps, threads, budget_s=100.0):
+    """Mean seconds per p_sample step of the oracle port at `sample_batch` images, after one warm-up
+    step; at most n_steps timed steps and at most ~budget_s seconds of timed CPU work.
+    Returns (seconds_per_step, steps_timed)."""
     from oracle import bbdm_oracle as O
     from bbdm_b200.unet import UNetModel
     torch.set_num_threads(threads)
@@ -165,14 +168,18 @@ def cpu_step_time(cfg, sample_batch, n_steps, threads):
     S, C = cfg["size"], cfg["channels"]
     y = synth((sample_batch, C, S, S), 1)
     x = synth((sample_batch, C, S, S), 2)
+    ctx = None if cfg["unet"]["condition_key"] == "nocond" else y
     times = []
     with torch.no_grad():
-        for i in range(n_steps + 1):                      # first iteration = warm-up
+        for i in range(max(1, n_steps) + 1):                      # first iteration = warm-up
             nz = torch.randn(x.shape)
             t0 = time.perf_counter()
-            x, _ = O.p_sample(sd, ocfg, bufs, steps, 3 + i, x, y, y, nz, prefix="")
+            x, _ = O.p_sample(sd, ocfg, bufs, steps, 3 + i, x, y, ctx, nz, prefix="")
             times.append(time.perf_counter() - t0)
-    return statistics.mean(times[1:]) if n_steps else times[0]
+            if i >= 1 and sum(times[1:]) + times[-1] > budget_s:
+                break
+    timed = times[1:]
+    return statistics.mean(timed), len(timed)
 
 
 def host_threads():
@@ -192,11 +199,11 @@ def run_reference_arm(args, cfg):
         return
     threads = host_threads()
     sb = 1 if cfg["batch"] > 4 else cfg["batch"]
-    per = cpu_step_time(cfg, sb, max(1, args.steps), threads)
+    per, n_timed = cpu_step_time(cfg, sb, max(1, args.steps), threads)
     scale = cfg["batch"] / sb
     ms = per * scale * 1e3
     val = 1e3 / ms
-    sample = (f"{max(1, args.steps)} p_sample step(s) on {sb} of the {cfg['batch']} images (time scaled x{scale:g}), "
+    sample = (f"{n_timed} p_sample step(s) (bounded to ~100 s of CPU work) on {sb} of the {cfg['batch']} images (time scaled x{scale:g}), "
               f"after 1 warm-up step; oracle port (torch CPU fp32), {threads} threads")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -387,7 +394,7 @@ def main():
         if not args.no_cpu_baseline:
             threads = host_threads()
             sb = 1 if B > 4 else B
-            per = cpu_step_time(cfg, sb, 1, threads)
+            per, _ = cpu_step_time(cfg, sb, 1, threads)
             scale = B / sb
             cpu = {"value": 1.0 / (per * scale), "unit": "steps/s", "cores": threads, "kind": "port",
                    "sample": f"1 p_sample step on {sb} of the {B} images (time scaled x{scale:g}) after 1 warm-up; "
