@@ -481,7 +481,14 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   p.tiles_h = (a->H + p.TH - 1) / p.TH;
   p.tiles_b = (a->B + p.TB - 1) / p.TB;
   p.n_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
-  const int BN = (a->Cout % 256 == 0) ? 256 : (a->Cout % 128 == 0 ? 128 : 64);
+  // N tile: the widest that divides Cout -- unless that leaves most SMs without a tile (small spatial
+  // extents / batches): then narrower tiles (more CTAs, each less efficient) finish sooner.
+  int BN = (a->Cout % 256 == 0) ? 256 : (a->Cout % 128 == 0 ? 128 : 64);
+  {
+    const int64_t m_tiles = (int64_t)p.n_tiles * (a->upsample2x ? 4 : 1);
+    const int64_t want = (int64_t)(0.7 * num_sms());
+    while (BN > 64 && m_tiles * (a->Cout / BN) < want) BN /= 2;
+  }
   // BBDM_CONV_BK=32: 256-wide N tiles in split mode use 32-channel K blocks (4-stage TMA ring instead of
   // 2).  Measured on B200 (round 1): the tensor pipe gets busier but the 1 kW power cap lowers the SM
   // clock by the same factor (1522 -> 1335 MHz), identical step time -- so 64 stays the default.
