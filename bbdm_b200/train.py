@@ -126,9 +126,12 @@ class GNActConv2dFn(torch.autograd.Function):
     stats + prep + tcgen05 conv; the backward adds the two-pass GroupNorm/SiLU/FiLM gradient kernels."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale, shift, weight, bias):
+    def forward(ctx, x, gamma, beta, scale, shift, weight, bias, resample=0):
+        """resample: 0 none, 1 nearest-2x up, 2 2x2 average pool -- applied between SiLU and the conv
+        (ResBlock(up/down), openaimodel.py:259-264)."""
         be = backend()
-        B, Cin, H, W = x.shape
+        B, Cin, Hs, Ws = x.shape
+        H, W = (Hs * 2, Ws * 2) if resample == 1 else ((Hs // 2, Ws // 2) if resample == 2 else (Hs, Ws))
         Cout, _, k, _ = weight.shape
         dev = x.device
         xn = _nhwc(x.detach())
@@ -142,7 +145,8 @@ class GNActConv2dFn(torch.autograd.Function):
         a_hi = torch.empty((B, H, W, Cin), dtype=torch.bfloat16, device=dev)
         a_lo = torch.empty_like(a_hi)
         be.prep(xn, None, groups=32, mean=mean, rstd=rstd, gamma=gamma.detach(), beta=beta.detach(), film_scale=fs,
-                film_shift=fh, film_stride=0 if fs is None else fs.shape[1], silu=True, act_hi=a_hi, act_lo=a_lo)
+                film_shift=fh, film_stride=0 if fs is None else fs.shape[1], silu=True, resample=resample,
+                act_hi=a_hi, act_lo=a_lo)
         w_hi = torch.empty((k * k, Cout, Cin), dtype=torch.bfloat16, device=dev)
         w_lo = torch.empty_like(w_hi)
         be.pack_weight_split(weight.detach().contiguous(), w_hi, w_lo)
@@ -152,6 +156,7 @@ class GNActConv2dFn(torch.autograd.Function):
         ctx.save_for_backward(xn, mean, rstd, gamma, beta, fs, fh, a_hi, a_lo, weight)
         ctx.has_bias = bias is not None
         ctx.shape = (B, H, W, Cin, Cout, k)
+        ctx.resample = resample
         return out.permute(0, 3, 1, 2)
 
     @staticmethod
@@ -162,6 +167,11 @@ class GNActConv2dFn(torch.autograd.Function):
         dev = dy.device
         da, dw, dbias = _conv_backward(be, ctx.shape, a_hi, a_lo, weight, dy, True, ctx.needs_input_grad[5],
                                        ctx.has_bias and ctx.needs_input_grad[6])
+        if ctx.resample == 1:        # adjoint of nearest-2x: sum the four children
+            da = da.view(B, H // 2, 2, W // 2, 2, Cin).sum(dim=(2, 4)).contiguous()
+        elif ctx.resample == 2:      # adjoint of the 2x2 mean: a quarter to each of the four parents
+            da = (0.25 * da).repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).contiguous()
+        H, W = xn.shape[1], xn.shape[2]
         g, b_ = gamma.detach(), beta.detach()
         fstride = 0 if fs is None else fs.shape[1]
         a12 = torch.empty((B, Cin, 2), dtype=torch.float32, device=dev)
@@ -180,19 +190,28 @@ class GNActConv2dFn(torch.autograd.Function):
         s2 = (gf * a2).view(B, 32, Cin // 32).sum(2).contiguous()
         dxn = torch.empty((B, H, W, Cin), dtype=torch.float32, device=dev)
         be.gn_bwd_apply(xn, da, 32, mean, rstd, g, b_, fs, fh, fstride, True, s1, s2, dxn)
-        return dxn.permute(0, 3, 1, 2), dgamma, dbeta, dscale, dshift, dw, dbias
+        return dxn.permute(0, 3, 1, 2), dgamma, dbeta, dscale, dshift, dw, dbias, None
 
 
-def gn_act_conv2d(norm, conv, x, scale=None, shift=None, enabled=True):
-    """conv(silu(norm(x) * (1 + scale) + shift)) -- fused tensor-core path when the shape qualifies."""
-    if enabled and native_ok(conv, x) and x.shape[1] % 32 == 0 and x.shape[1] <= 4096:
+def gn_act_conv2d(norm, conv, x, scale=None, shift=None, enabled=True, resample=0):
+    """conv(resample(silu(norm(x) * (1 + scale) + shift))) -- fused tensor-core path when the shape qualifies."""
+    B, _, Hs, Ws = x.shape
+    H, W = (Hs * 2, Ws * 2) if resample == 1 else ((Hs // 2, Ws // 2) if resample == 2 else (Hs, Ws))
+    probe = x if resample == 0 else x.new_empty((B, x.shape[1], H, W))       # shape check at the conv's resolution
+    if enabled and native_ok(conv, probe) and x.shape[1] % 32 == 0 and x.shape[1] <= 4096 and \
+            (resample != 2 or (Hs % 2 == 0 and Ws % 2 == 0)):
         sc = None if scale is None else scale.reshape(scale.shape[0], -1)
         sh = None if shift is None else shift.reshape(shift.shape[0], -1)
-        return GNActConv2dFn.apply(x, norm.weight, norm.bias, sc, sh, conv.weight, conv.bias)
+        return GNActConv2dFn.apply(x, norm.weight, norm.bias, sc, sh, conv.weight, conv.bias, resample)
     h = norm(x)
     if scale is not None:
         h = h * (1 + scale) + shift
-    return conv2d(conv, torch.nn.functional.silu(h), enabled)
+    h = torch.nn.functional.silu(h)
+    if resample == 1:
+        h = torch.nn.functional.interpolate(h, scale_factor=2, mode="nearest")
+    elif resample == 2:
+        h = torch.nn.functional.avg_pool2d(h, 2)
+    return conv2d(conv, h, enabled)
 
 
 def conv2d(conv: torch.nn.Conv2d, x: torch.Tensor, enabled: bool = True) -> torch.Tensor:

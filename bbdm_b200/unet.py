@@ -129,13 +129,8 @@ class ResBlock(TimestepBlock):
         Functions over the tensor-core kernels (bbdm_b200/train.py) when shapes qualify."""
         nat = NATIVE_TRAIN_CONV
         if self.up or self.down:
-            h = self.in_layers[1](self.in_layers[0](x))
-            if self.up:
-                h = F.interpolate(h, scale_factor=2, mode="nearest")
-                x = F.interpolate(x, scale_factor=2, mode="nearest")
-            else:
-                h, x = F.avg_pool2d(h, 2), F.avg_pool2d(x, 2)
-            h = _conv2d(self.in_layers[2], h, nat)
+            h = _gn_act_conv2d(self.in_layers[0], self.in_layers[2], x, None, None, nat, resample=1 if self.up else 2)
+            x = F.interpolate(x, scale_factor=2, mode="nearest") if self.up else F.avg_pool2d(x, 2)
         else:
             h = _gn_act_conv2d(self.in_layers[0], self.in_layers[2], x, None, None, nat)
         e = self.emb_layers(emb).type(h.dtype)[:, :, None, None]

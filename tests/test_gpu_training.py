@@ -153,3 +153,27 @@ def test_gn_act_conv_function_gradients(B, H, W, C, Cout, film):
         pairs += [("scale", scale, sd), ("shift", shift, hd)]
     for name, a, r in pairs:
         assert rel_dev(a.grad, r.grad) < 5e-5, (name, rel_dev(a.grad, r.grad))
+
+
+@pytest.mark.parametrize("resample", [1, 2])
+def test_gn_act_conv_function_with_resampling(resample):
+    """up / down ResBlock in_layers: GN -> SiLU -> (nearest-2x | 2x2 mean) -> conv, fused, all gradients."""
+    from bbdm_b200.train import GNActConv2dFn
+    B, C, Cout, Hs = 2, 128, 128, 16
+    mk = lambda t: t.to(DEV).requires_grad_(True)
+    x = mk(rnd((B, C, Hs, Hs), 20) + 0.1)
+    gamma, beta = mk(1 + 0.1 * rnd((C,), 21)), mk(0.1 * rnd((C,), 22))
+    w, b = mk(rnd((Cout, C, 3, 3), 23, 0.05)), mk(rnd((Cout,), 24, 0.1))
+    H = Hs * 2 if resample == 1 else Hs // 2
+    gy = rnd((B, Cout, H, H), 25, 0.2).to(DEV)
+    y = GNActConv2dFn.apply(x, gamma, beta, None, None, w, b, resample)
+    y.backward(gy)
+    d = lambda t: t.detach().double().cpu().requires_grad_(True)
+    xd, gd, bd, wd, bbd = d(x), d(gamma), d(beta), d(w), d(b)
+    h = F.silu(F.group_norm(xd, 32, gd, bd, 1e-5))
+    h = F.interpolate(h, scale_factor=2, mode="nearest") if resample == 1 else F.avg_pool2d(h, 2)
+    yd = F.conv2d(h, wd, bbd, padding=1)
+    yd.backward(gy.double().cpu())
+    assert rel_dev(y, yd) < 3e-5
+    for name, a, r in [("x", x, xd), ("gamma", gamma, gd), ("beta", beta, bd), ("w", w, wd), ("b", b, bbd)]:
+        assert rel_dev(a.grad, r.grad) < 5e-5, (name, rel_dev(a.grad, r.grad))
