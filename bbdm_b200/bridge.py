@@ -123,7 +123,8 @@ class BridgeOps:
         eng = m.denoise_fn.engine()
         ctx_is_y = context is y or context is None
         key = (tuple(y.shape), y.device, bool(clip), eng.generation, m.objective,
-               None if context is None else tuple(context.shape), ctx_is_y)
+               None if context is None else tuple(context.shape), ctx_is_y,
+               eng.pool_serial(y.device, (y.shape[0], y.shape[2], y.shape[3])))
         g = self._graphs.get(key)
         if g is not None:
             return g

@@ -34,9 +34,13 @@ class _Pool:
     call, so after the first call no allocation happens and every intermediate keeps a stable
     address (required for CUDA-graph replay, avoids allocator traffic)."""
 
+    _serial = 0
+
     def __init__(self, backend, device):
         self.be, self.device, self.free = backend, device, {}
         self.bytes = 0
+        _Pool._serial += 1
+        self.serial = _Pool._serial          # identity of this set of buffers (captured graphs key on it)
 
     def get(self, shape, dtype=torch.float32):
         key = (tuple(shape), dtype)
@@ -177,11 +181,24 @@ class UNetEngine:
             self._table = tab.to(dev).contiguous()
 
     # ------------------------------------------------------------------------------ helpers
-    def _pool(self, device):
-        p = self._pools.get(device)
+    def _pool(self, device, shape_key=None):
+        """Intermediate-buffer pool for one (device, input shape).  At most two shapes stay resident (the
+        steady batch and e.g. a smaller last batch of sample_to_eval); older pools are dropped so a
+        long-lived model does not accumulate HBM across shape changes."""
+        key = (device, shape_key)
+        p = self._pools.pop(key, None)
         if p is None:
-            p = self._pools[device] = _Pool(self.be, device)
+            p = _Pool(self.be, device)
+            while len(self._pools) >= 2:
+                self._pools.pop(next(iter(self._pools)))       # evict least recently used
+        self._pools[key] = p                                   # (re)insert as most recent
         return p
+
+    def pool_serial(self, device, shape_key):
+        return self._pool(device, shape_key).serial
+
+    def pool_bytes(self):
+        return sum(p.bytes for p in self._pools.values())
 
     def _stats(self, pool, src1, src2):
         B = src1.shape[0]
@@ -444,9 +461,9 @@ class UNetEngine:
             self.refresh_weights()
         w = self._w
         dev = x.device
-        pool = self._pool(dev)
         x = x.contiguous().float()
         B, Cx, H, W = x.shape
+        pool = self._pool(dev, (B, H, W))
         ctx = None
         if u.condition_key != "nocond":
             ctx = context.contiguous().float()

@@ -410,6 +410,7 @@ def main():
                            "l2": "working set larger than L2: every step streams the 0.95 GB of split-bf16 weights"
                                  + (" and 0.5-1.3 GB activation tensors" if args.config == "cfg2" else ""),
                            "graph_replay_ms_per_step": graph_ms,
+                           "activation_pool_gb": net.denoise_fn.engine().pool_bytes() / 1e9,
                            "img_steps_per_s": world * B * 1e3 / ms_dev,
                            "unet_tflops_per_s": world * cfg["flops_per_step"] / (ms_dev * 1e-3) / 1e12},
                 "e2e": {"value": world * 1e3 / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": 2 * nbytes,

@@ -39,7 +39,7 @@ def test_engine_wiring_matches_reference_fixture(tag, tol, expect_umma):
     assert rel_dev(out, g["unet_out"]) < tol
     assert ("conv_umma" in be.calls) == expect_umma
     # second call: no new allocations (stable addresses for CUDA-graph replay), same result
-    pool = eng._pool(g["x"].device)
+    pool = eng._pool(g["x"].device, tuple(g["x"].shape[i] for i in (0, 2, 3)))
     nbytes = pool.bytes
     out2 = eng.forward(g["x"], g["t"], ctx)
     assert pool.bytes == nbytes
@@ -68,3 +68,13 @@ def test_unet_rejects_cpu_inference():
     net = build("tiny_latent")
     with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
         net(torch.zeros(1, 4, 16, 16), timesteps=torch.zeros(1, dtype=torch.long))
+
+
+def test_buffer_pools_are_bounded_across_shape_changes():
+    net = build("tiny_latent")
+    eng = UNetEngine(net, backend=EmuBackend())
+    t = torch.zeros(1, dtype=torch.long)
+    for b in (1, 2, 3, 2, 1):
+        eng.forward(torch.zeros(b, 4, 16, 16), t.expand(b).contiguous(), None)
+        assert len(eng._pools) <= 2
+    assert eng.pool_bytes() > 0
