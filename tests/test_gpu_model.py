@@ -135,3 +135,59 @@ def test_cuda_graph_loop_equals_eager_loop():
     a3, b3 = run(False), run(True)
     assert torch.equal(a3, b3) and not torch.equal(a3, a2)
     net._bridge.backend().check_fault()
+
+
+def _pixel_unet(image_size):
+    import copy
+    u = copy.deepcopy(UNET_CONFIGS["cfg1"])
+    u["image_size"] = image_size
+    return u
+
+
+def test_full_resolution_batch_independence_and_determinism():
+    """BASELINE configs[1] resolution (256x256 pixel BBDM UNet, 237 M parameters), size-independent
+    properties: (1) samples of a batch do not interact -- UNet(x)[i] is BIT-identical to UNet(x[i:i+1])
+    (GroupNorm statistics and every tile reduction are per image, in a fixed order); (2) run-to-run
+    determinism; (3) the bridge update is exactly linear in the supplied noise."""
+    from model.BrownianBridge.BrownianBridgeModel import BrownianBridgeModel
+    net = BrownianBridgeModel(bb_namespace(_pixel_unet(256))).eval()
+    shapes = {k: tuple(v.shape) for k, v in net.denoise_fn.state_dict().items()}
+    net.denoise_fn.load_state_dict(fill_state_dict(shapes, seed=1234))
+    net = net.cuda()
+    x = synth_images((3, 3, 256, 256), 21).cuda()
+    y = synth_images((3, 3, 256, 256), 22).cuda()
+    t = torch.tensor([999, 500, 0], device="cuda")
+    with torch.no_grad():
+        full = net.denoise_fn(x, timesteps=t, context=y).clone()
+        again = net.denoise_fn(x, timesteps=t, context=y).clone()
+        assert torch.equal(full, again)
+        for i in range(3):
+            one = net.denoise_fn(x[i:i + 1], timesteps=t[i:i + 1], context=y[i:i + 1])
+            assert torch.equal(one[0], full[i]), i
+    assert torch.isfinite(full).all() and float(full.abs().max()) > 0
+    n1 = torch.randn_like(x)
+    a, _ = net.p_sample(x, y, y, 7, noise=n1)
+    b, _ = net.p_sample(x, y, y, 7, noise=torch.zeros_like(x))
+    c, _ = net.p_sample(x, y, y, 7, noise=2 * n1)
+    assert rel_dev(c - b, 2 * (a - b)) < 1e-6
+    net._bridge.backend().check_fault()
+
+
+def test_half_resolution_pixel_model_against_oracle():
+    """128x128 pixel BBDM (full channel widths), one p_sample against the CPU oracle computed on the spot."""
+    from model.BrownianBridge.BrownianBridgeModel import BrownianBridgeModel
+    u = _pixel_unet(128)
+    net = BrownianBridgeModel(bb_namespace(u)).eval()
+    shapes = {k: tuple(v.shape) for k, v in net.denoise_fn.state_dict().items()}
+    sd = fill_state_dict(shapes, seed=1234)
+    net.denoise_fn.load_state_dict(sd)
+    net = net.cuda()
+    xt, y = synth_images((1, 3, 128, 128), 31), synth_images((1, 3, 128, 128), 32)
+    nz = torch.randn(1, 3, 128, 128, generator=torch.Generator().manual_seed(33))
+    bufs, steps = O.make_schedule()
+    torch.set_num_threads(min(64, os.cpu_count() or 8))
+    want, _ = O.p_sample(sd, O.unet_cfg(**u), bufs, steps, 150, xt, y, y, nz, prefix="")
+    got, _ = net.p_sample(xt.cuda(), y.cuda(), y.cuda(), 150, noise=nz.cuda())
+    d = rel_dev(got, want)
+    print(f"\n[pixel 128x128] p_sample rel dev vs oracle {d:.3e}")
+    assert d < TOL_PSAMPLE
