@@ -29,6 +29,7 @@ SYMBOLS = [
     "bbdm_pack_weight_f32", "bbdm_conv_umma", "bbdm_conv_direct",
     "bbdm_attention", "bbdm_attention_split", "bbdm_attention_tc", "bbdm_conv_umma_geometry", "bbdm_gn_finalize_partials",
     "bbdm_split_grad", "bbdm_conv_wgrad_workspace", "bbdm_conv_wgrad", "bbdm_gn_bwd_reduce", "bbdm_gn_bwd_apply",
+    "bbdm_conv_wgrad_direct",
 ]
 
 
@@ -105,6 +106,7 @@ def load():
     lib.bbdm_split_grad.argtypes = [vp, i64, i, vp, vp, vp, vp, vp, vp, vp]
     lib.bbdm_conv_wgrad_workspace.argtypes = [i, i, i, i, i, i, C.POINTER(i), C.POINTER(i64)]
     lib.bbdm_conv_wgrad.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, vp, vp, vp]
+    lib.bbdm_conv_wgrad_direct.argtypes = [vp, vp, i, i, i, i, i, i, vp, vp, i64, vp]
     lib.bbdm_gn_bwd_reduce.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp, vp, i64, i, vp, vp, vp]
     lib.bbdm_gn_bwd_apply.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp, vp, i64, i, vp, vp, vp, vp]
     lib.bbdm_attention_split.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp]
@@ -287,6 +289,13 @@ class CudaBackend:
     def conv_wgrad(self, g_hi_t, g_lo_t, a_hi, a_lo, B, H, W, Cin, Cout, taps, dw, workspace):
         check(self.lib.bbdm_conv_wgrad(ptr(g_hi_t), ptr(g_lo_t), ptr(a_hi), ptr(a_lo), B, H, W, Cin, Cout, taps,
                                        ptr(_req(dw)), ptr(_req(workspace)), stream()))
+        LAUNCHES["n"] += 2
+
+    def conv_wgrad_direct(self, dy, x, k, dw, workspace):
+        B, H, W, Cin = x.shape
+        Cout = dy.shape[3]
+        check(self.lib.bbdm_conv_wgrad_direct(ptr(_req(dy)), ptr(_req(x)), B, H, W, Cin, Cout, k, ptr(_req(dw)),
+                                              ptr(_req(workspace)), workspace.numel(), stream()))
         LAUNCHES["n"] += 2
 
     def gn_bwd_reduce(self, x, da, groups, mean, rstd, gamma, beta, fscale, fshift, fstride, silu, a12, ws):

@@ -214,8 +214,65 @@ def gn_act_conv2d(norm, conv, x, scale=None, shift=None, enabled=True, resample=
     return conv2d(conv, h, enabled)
 
 
+class SmallConv2dFn(torch.autograd.Function):
+    """The UNet stem / head (3..32 channels on one side): exact fp32 on CUDA cores -- forward and data
+    gradient through bbdm_conv_direct, weight gradient through bbdm_conv_wgrad_direct."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        be = backend()
+        B, Cin, H, W = x.shape
+        Cout, _, k, _ = weight.shape
+        dev = x.device
+        xn = _nhwc(x.detach()).contiguous()
+        wp = torch.empty((k * k, Cin, Cout), dtype=torch.float32, device=dev)
+        be.pack_weight_f32(weight.detach().contiguous(), wp)
+        out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=dev)
+        be.conv_direct(xn, wp, None if bias is None else bias.detach(), None, out, Cout, k, 1)
+        ctx.save_for_backward(xn, weight)
+        ctx.has_bias = bias is not None
+        ctx.k = k
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        be = backend()
+        xn, weight = ctx.saved_tensors
+        k = ctx.k
+        B, H, W, Cin = xn.shape
+        Cout = weight.shape[0]
+        dev = dy.device
+        dyn = _nhwc(dy).contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wd = weight.detach().flip(2, 3).transpose(0, 1).contiguous()          # [Cin, Cout, k, k]
+            wdp = torch.empty((k * k, Cout, Cin), dtype=torch.float32, device=dev)
+            be.pack_weight_f32(wd, wdp)
+            dxn = torch.empty((B, H, W, Cin), dtype=torch.float32, device=dev)
+            be.conv_direct(dyn, wdp, None, None, dxn, Cin, k, 1)
+            dx = dxn.permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            n = k * k * Cin * Cout
+            ws = torch.empty((512 * n,), dtype=torch.float32, device=dev)
+            dw = torch.empty((Cout, Cin, k, k), dtype=torch.float32, device=dev)
+            be.conv_wgrad_direct(dyn, xn, k, dw, ws)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dyn.sum(dim=(0, 1, 2))
+        return dx, dw, db
+
+
+def small_ok(conv: torch.nn.Conv2d, x: torch.Tensor) -> bool:
+    k = conv.kernel_size
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and k in ((1, 1), (3, 3))
+            and conv.stride == (1, 1) and conv.padding == (k[0] // 2, k[0] // 2) and conv.groups == 1
+            and conv.dilation == (1, 1) and conv.in_channels * conv.out_channels <= 1024
+            and min(conv.in_channels, conv.out_channels) <= 32)
+
+
 def conv2d(conv: torch.nn.Conv2d, x: torch.Tensor, enabled: bool = True) -> torch.Tensor:
     """nn.Conv2d call with the tensor-core autograd path when the shape qualifies."""
     if enabled and native_ok(conv, x):
         return Conv2dFn.apply(x, conv.weight, conv.bias)
+    if enabled and small_ok(conv, x):
+        return SmallConv2dFn.apply(x, conv.weight, conv.bias)
     return conv(x)

@@ -291,10 +291,10 @@ class UNetModel(nn.Module):
         if self.condition_key != "nocond":
             x = torch.cat([x, context], dim=1)
         h, hs = x, []
-        for m in self.input_blocks:
-            h = m(h, emb)
+        for i, m in enumerate(self.input_blocks):
+            h = _conv2d(m[0], h, NATIVE_TRAIN_CONV) if i == 0 else m(h, emb)     # [0] is the stem conv
             hs.append(h)
         h = self.middle_block(h, emb)
         for m in self.output_blocks:
             h = m(torch.cat([h, hs.pop()], dim=1), emb)
-        return self.out(h)
+        return _conv2d(self.out[2], self.out[1](self.out[0](h)), NATIVE_TRAIN_CONV)

@@ -260,6 +260,13 @@ int bbdm_conv_wgrad(const void* g_hi_t, const void* g_lo_t, const void* a_hi, co
                     int B, int H, int W, int Cin, int Cout, int taps, float* dw, float* workspace,
                     void* stream);
 
+/* Weight gradient of the small-channel fp32 convolutions (UNet stem / head; Cin*Cout <= 1024):
+ * dy NHWC [B,H,W,Cout], x NHWC [B,H,W,Cin] fp32, stride 1, pad k/2 -> dw OIHW fp32 (overwritten).
+ * workspace: any multiple of k*k*Cin*Cout floats (more = more CTAs, up to 1024); fixed-order reduce.
+ * (The data gradient of these layers is bbdm_conv_direct with the flipped/transposed weights.) */
+int bbdm_conv_wgrad_direct(const float* dy, const float* x, int B, int H, int W, int Cin, int Cout, int k,
+                           float* dw, float* workspace, int64_t workspace_floats, void* stream);
+
 /* Backward of the fused operand preparation  a = silu( (gamma*xh + beta) * (1+scale) + shift ),
  * xh = (x-mean)*rstd  (training path; replaces the autograd of GroupNorm32 + SiLU + scale-shift,
  * openaimodel.py:205-206,229-230,270-274).  Two HBM-bound passes over (x, dA):

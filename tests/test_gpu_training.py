@@ -177,3 +177,24 @@ def test_gn_act_conv_function_with_resampling(resample):
     assert rel_dev(y, yd) < 3e-5
     for name, a, r in [("x", x, xd), ("gamma", gamma, gd), ("beta", beta, bd), ("w", w, wd), ("b", b, bbd)]:
         assert rel_dev(a.grad, r.grad) < 5e-5, (name, rel_dev(a.grad, r.grad))
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,need_dx", [(2, 16, 16, 6, 128, 3, False), (2, 16, 16, 128, 3, 3, True),
+                                                       (1, 8, 12, 16, 16, 3, True), (2, 8, 8, 4, 64, 1, True)])
+def test_small_conv_function_gradients(B, H, W, Cin, Cout, k, need_dx):
+    """Stem / head style convolutions (few channels on one side): exact-fp32 forward, dgrad, wgrad."""
+    from bbdm_b200.train import SmallConv2dFn
+    x = rnd((B, Cin, H, W), 30).to(DEV).requires_grad_(need_dx)
+    w = rnd((Cout, Cin, k, k), 31, 0.05).to(DEV).requires_grad_(True)
+    b = rnd((Cout,), 32, 0.1).to(DEV).requires_grad_(True)
+    gy = rnd((B, Cout, H, W), 33, 0.2).to(DEV)
+    y = SmallConv2dFn.apply(x, w, b)
+    y.backward(gy)
+    xd = x.detach().double().cpu().requires_grad_(need_dx)
+    wd, bd = w.detach().double().cpu().requires_grad_(True), b.detach().double().cpu().requires_grad_(True)
+    yd = F.conv2d(xd, wd, bd, padding=k // 2)
+    yd.backward(gy.double().cpu())
+    assert rel_dev(y, yd) < 2e-6
+    assert rel_dev(w.grad, wd.grad) < 2e-6 and rel_dev(b.grad, bd.grad) < 2e-6
+    if need_dx:
+        assert rel_dev(x.grad, xd.grad) < 2e-6
