@@ -199,7 +199,7 @@ extern "C" int bbdm_conv_wgrad_direct(const float* dy, const float* x, int B, in
   const int64_t P = (int64_t)B * H * W;
   const int64_t n = (int64_t)k * k * Cin * Cout;
   int64_t nblk = workspace_floats / n;
-  if (nblk > 1024) nblk = 1024;
+  if (nblk > 4096) nblk = 4096;
   if (nblk > P) nblk = P;
   BBDM_REQUIRE(nblk >= 1, "conv_wgrad_direct: workspace too small (need >= %lld floats)", (long long)n);
   const int ppb = (int)((P + nblk - 1) / nblk);

@@ -253,7 +253,7 @@ class SmallConv2dFn(torch.autograd.Function):
             dx = dxn.permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
             n = k * k * Cin * Cout
-            ws = torch.empty((512 * n,), dtype=torch.float32, device=dev)
+            ws = torch.empty((2048 * n,), dtype=torch.float32, device=dev)
             dw = torch.empty((Cout, Cin, k, k), dtype=torch.float32, device=dev)
             be.conv_wgrad_direct(dyn, xn, k, dw, ws)
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -267,6 +267,19 @@ def small_ok(conv: torch.nn.Conv2d, x: torch.Tensor) -> bool:
             and conv.stride == (1, 1) and conv.padding == (k[0] // 2, k[0] // 2) and conv.groups == 1
             and conv.dilation == (1, 1) and conv.in_channels * conv.out_channels <= 1024
             and min(conv.in_channels, conv.out_channels) <= 32)
+
+
+def conv1x1(conv1d: torch.nn.Conv1d, x4: torch.Tensor, enabled: bool = True):
+    """nn.Conv1d(k=1) of AttentionBlock (qkv / proj_out, openaimodel.py:307,315) applied to a [B,C,H,W]
+    tensor as a 1x1 convolution on the tensor-core autograd path; returns [B,Cout,H,W] or None if the
+    shape does not qualify (caller falls back to the module)."""
+    B, C, H, W = x4.shape
+    Cout = conv1d.out_channels
+    ok = (enabled and x4.is_cuda and x4.dtype == torch.float32 and conv1d.kernel_size == (1,) and C % 64 == 0
+          and Cout % 64 == 0 and W >= 4 and (B * H * W) % 64 == 0 and _box64_ok(B, H, W))
+    if not ok:
+        return None
+    return Conv2dFn.apply(x4, conv1d.weight.unsqueeze(-1), conv1d.bias)
 
 
 def conv2d(conv: torch.nn.Conv2d, x: torch.Tensor, enabled: bool = True) -> torch.Tensor:

@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .train import conv2d as _conv2d, gn_act_conv2d as _gn_act_conv2d
+from .train import conv1x1 as _conv1x1, conv2d as _conv2d, gn_act_conv2d as _gn_act_conv2d
 
 # training path: ResBlock convolutions on the tcgen05 fwd / dgrad / wgrad kernels (bbdm_b200/train.py);
 # set False to run the whole training graph on stock PyTorch kernels
@@ -171,7 +171,12 @@ class AttentionBlock(nn.Module):
         # (the reference wraps this in its CheckpointFunction, util.py:119-148: same values)
         b, c, *spatial = x.shape
         xf = x.reshape(b, c, -1)
-        qkv = self.qkv(self.norm(xf))
+        qkv = None
+        if x.dim() == 4:          # qkv 1x1 on the tensor-core autograd path when the shape qualifies
+            q4 = _conv1x1(self.qkv, self.norm(x), NATIVE_TRAIN_CONV)
+            qkv = None if q4 is None else q4.reshape(b, 3 * c, -1)
+        if qkv is None:
+            qkv = self.qkv(self.norm(xf))
         bs, width, length = qkv.shape
         ch = width // (3 * self.num_heads)
         if self.new_order:
@@ -182,6 +187,10 @@ class AttentionBlock(nn.Module):
         w = torch.einsum("bct,bcs->bts", q * scale, k * scale)
         w = torch.softmax(w.float(), dim=-1).type(w.dtype)
         a = torch.einsum("bts,bcs->bct", w, v).reshape(bs, -1, length)
+        if x.dim() == 4:
+            p4 = _conv1x1(self.proj_out, a.reshape(b, c, *spatial), NATIVE_TRAIN_CONV)
+            if p4 is not None:
+                return x + p4
         return (xf + self.proj_out(a)).reshape(b, c, *spatial)
 
 

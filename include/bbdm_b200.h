@@ -262,7 +262,7 @@ int bbdm_conv_wgrad(const void* g_hi_t, const void* g_lo_t, const void* a_hi, co
 
 /* Weight gradient of the small-channel fp32 convolutions (UNet stem / head; Cin*Cout <= 1024):
  * dy NHWC [B,H,W,Cout], x NHWC [B,H,W,Cin] fp32, stride 1, pad k/2 -> dw OIHW fp32 (overwritten).
- * workspace: any multiple of k*k*Cin*Cout floats (more = more CTAs, up to 1024); fixed-order reduce.
+ * workspace: any multiple of k*k*Cin*Cout floats (more = more CTAs, up to 4096); fixed-order reduce.
  * (The data gradient of these layers is bbdm_conv_direct with the flipped/transposed weights.) */
 int bbdm_conv_wgrad_direct(const float* dy, const float* x, int B, int H, int W, int Cin, int Cout, int k,
                            float* dw, float* workspace, int64_t workspace_floats, void* stream);
