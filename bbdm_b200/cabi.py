@@ -25,7 +25,7 @@ SYMBOLS = [
     "bbdm_abi_version", "bbdm_last_error", "bbdm_device_info", "bbdm_check_device_fault",
     "bbdm_bridge_q_sample", "bbdm_bridge_p_sample", "bbdm_bridge_p_sample_dev", "bbdm_nchw_to_nhwc_cat", "bbdm_nhwc_to_nchw",
     "bbdm_gather_rows", "bbdm_linear_f32", "bbdm_gn_stats", "bbdm_prep_operand",
-    "bbdm_pack_weight_split", "bbdm_pack_weight_split_padded", "bbdm_pack_weight_split_taps",
+    "bbdm_pack_weight_split", "bbdm_pack_weight_split_padded", "bbdm_pack_weight_split_taps", "bbdm_pack_weight_split_dgrad",
     "bbdm_pack_weight_f32", "bbdm_conv_umma", "bbdm_conv_direct",
     "bbdm_attention", "bbdm_attention_split", "bbdm_attention_tc", "bbdm_conv_umma_geometry", "bbdm_gn_finalize_partials",
     "bbdm_split_grad", "bbdm_conv_wgrad_workspace", "bbdm_conv_wgrad", "bbdm_gn_bwd_reduce", "bbdm_gn_bwd_apply",
@@ -96,6 +96,7 @@ def load():
     lib.bbdm_prep_operand.argtypes = [C.POINTER(PrepArgs), vp]
     lib.bbdm_pack_weight_split.argtypes = [vp, i, i, i, vp, vp, vp]
     lib.bbdm_pack_weight_split_padded.argtypes = [vp, i, i, i, i, vp, vp, vp]
+    lib.bbdm_pack_weight_split_dgrad.argtypes = [vp, i, i, i, vp, vp, vp]
     lib.bbdm_pack_weight_split_taps.argtypes = [vp, i, i, i, vp, vp, vp]
     lib.bbdm_pack_weight_f32.argtypes = [vp, i, i, i, vp, vp]
     lib.bbdm_conv_umma.argtypes = [C.POINTER(ConvArgs), vp]
@@ -237,6 +238,12 @@ class CudaBackend:
         Cout, Cin, k = w.shape[0], w.shape[1], (w.shape[2] if w.dim() > 2 else 1)
         check(self.lib.bbdm_pack_weight_split_padded(ptr(_req(w)), Cout, Cin, k, hi.shape[1], ptr(hi), ptr(lo),
                                                      stream()))
+        LAUNCHES["n"] += 1
+
+    def pack_weight_split_dgrad(self, w, hi, lo):
+        """w [Cout,Cin,k,k] -> hi/lo [k*k, Cin, Cout] bf16: flipped kernel, swapped channels."""
+        Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
+        check(self.lib.bbdm_pack_weight_split_dgrad(ptr(_req(w)), Cout, Cin, k, ptr(hi), ptr(lo), stream()))
         LAUNCHES["n"] += 1
 
     def pack_weight_split_taps(self, w, hi, lo):

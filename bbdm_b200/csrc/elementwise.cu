@@ -175,6 +175,25 @@ pack_weight_split_kernel(const float* __restrict__ w, int Cout, int Cin, int kk,
   }
 }
 
+// data-gradient layout straight from OIHW: dst[t'][ci][co] = w[co][ci][kk-1-t']  (kernel flipped,
+// Cin/Cout swapped) -- the conv that maps dY to dX is bbdm_conv_umma with these planes
+__global__ void __launch_bounds__(256)
+pack_weight_split_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int kk,
+                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int64_t n = (int64_t)kk * Cout * Cin;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const int ci = (int)((i / Cout) % Cin);
+    const int tap = (int)(i / ((int64_t)Cin * Cout));
+    const float v = w[((int64_t)co * Cin + ci) * kk + (kk - 1 - tap)];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 pack_weight_f32_kernel(const float* __restrict__ w, int Cout, int Cin, int kk, float* __restrict__ out) {
   const int64_t n = (int64_t)kk * Cout * Cin;
@@ -319,6 +338,15 @@ int bbdm_pack_weight_split_taps(const float* w, int Cout, int Cin, int taps, voi
   const int64_t n = (int64_t)taps * Cout * Cin;
   pack_weight_split_kernel<<<grid_for(n, 256, num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(
       w, Cout, Cin, taps, Cout, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo);
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
+int bbdm_pack_weight_split_dgrad(const float* w, int Cout, int Cin, int k, void* w_hi, void* w_lo, void* stream) {
+  BBDM_REQUIRE(w && w_hi && w_lo && Cout > 0 && Cin > 0 && (k == 1 || k == 3), "pack_weight_split_dgrad: bad args");
+  const int64_t n = (int64_t)k * k * Cout * Cin;
+  pack_weight_split_dgrad_kernel<<<grid_for(n, 256, num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(
+      w, Cout, Cin, k * k, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo);
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
 }

@@ -105,10 +105,10 @@ def _conv_backward(be, ctx_shape, a_hi, a_lo, weight, dy, need_dx, need_dw, need
     be.split_grad(dyn, g_hi, g_lo, gt_hi, gt_lo, dbias, ws_b)
     dxn = None
     if need_dx:
-        wd = weight.detach().flip(2, 3).transpose(0, 1).contiguous()          # [Cin, Cout, k, k]
+        # data gradient = the same conv with the kernel flipped and Cin/Cout swapped
         wd_hi = torch.empty((k * k, Cin, Cout), dtype=torch.bfloat16, device=dev)
         wd_lo = torch.empty_like(wd_hi)
-        be.pack_weight_split(wd, wd_hi, wd_lo)
+        be.pack_weight_split_dgrad(weight.detach().contiguous(), wd_hi, wd_lo)
         dxn = torch.empty((B, H, W, Cin), dtype=torch.float32, device=dev)
         be.conv_umma(B=B, H=H, W=W, Cin=Cout, Cout=Cin, taps=k * k, a_hi=g_hi, a_lo=g_lo, w_hi=wd_hi, w_lo=wd_lo,
                      out=dxn, passes=3)

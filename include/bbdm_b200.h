@@ -166,6 +166,10 @@ int bbdm_pack_weight_split_padded(const float* w, int Cout, int Cin, int k, int 
  * phase taps of the fused-upsample conv, BbdmConvArgs.upsample2x). */
 int bbdm_pack_weight_split_taps(const float* w, int Cout, int Cin, int taps, void* w_hi, void* w_lo,
                                 void* stream);
+/* Data-gradient planes straight from OIHW: hi/lo [k*k][Cin][Cout], kernel flipped and Cin/Cout
+ * swapped, so that dX = bbdm_conv_umma(dY planes, these planes) (training backward). */
+int bbdm_pack_weight_split_dgrad(const float* w, int Cout, int Cin, int k, void* w_hi, void* w_lo,
+                                 void* stream);
 int bbdm_pack_weight_f32(const float* w, int Cout, int Cin, int k, float* out, void* stream);
 
 enum { BBDM_RES_NONE = 0, BBDM_RES_SAME = 1, BBDM_RES_UP2 = 2, BBDM_RES_DOWN2 = 3 };
