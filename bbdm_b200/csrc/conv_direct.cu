@@ -175,12 +175,18 @@ conv_wgrad_direct_kernel(const float* __restrict__ dy, const float* __restrict__
   }
 }
 
+// one warp per output element: lanes stride over the partial blocks, fixed-order shuffle tree (fp64)
 __global__ void __launch_bounds__(256)
 wgrad_direct_reduce_kernel(const float* __restrict__ part, int nblk, int taps, int Cout, int Cin, float* __restrict__ dw) {
   const int64_t n = (int64_t)taps * Cout * Cin;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int kblk = 0; kblk < nblk; ++kblk) s += (double)part[(int64_t)kblk * n + i];
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int kblk = lane; kblk < nblk; kblk += 32) s += (double)part[(int64_t)kblk * n + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
     const int ci = (int)(i % Cin);
     const int co = (int)((i / Cin) % Cout);
     const int tap = (int)(i / ((int64_t)Cin * Cout));
@@ -207,7 +213,7 @@ extern "C" int bbdm_conv_wgrad_direct(const float* dy, const float* x, int B, in
   cudaStream_t s = (cudaStream_t)stream;
   bbdm::conv_wgrad_direct_kernel<<<(unsigned)nblk, 256, 0, s>>>(dy, x, workspace, B, H, W, Cin, Cout, k, ppb);
   BBDM_LAUNCH_CHECK();
-  bbdm::wgrad_direct_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(workspace, (int)nblk, k * k, Cout, Cin, dw);
+  bbdm::wgrad_direct_reduce_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(workspace, (int)nblk, k * k, Cout, Cin, dw);
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
 }

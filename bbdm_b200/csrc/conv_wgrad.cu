@@ -218,17 +218,19 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_con
   }
 }
 
-// sum the split-K partials in a fixed order; write OIHW:  dW[co][ci][tap]
+// sum the split-K partials in a fixed order; write OIHW:  dW[co][ci][tap].
+// thread = one (co, ci) pair, all taps: partial reads coalesced along ci, each thread writes its
+// `taps` consecutive output floats.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int taps, int Cout, int Cin, float* __restrict__ dw) {
-  const int64_t n = (int64_t)taps * Cout * Cin;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += partial[(int64_t)k * n + i];
-    const int ci = (int)(i % Cin);
-    const int co = (int)((i / Cin) % Cout);
-    const int tap = (int)(i / ((int64_t)Cin * Cout));
-    dw[((int64_t)co * Cin + ci) * taps + tap] = s;
+  const int64_t pairs = (int64_t)Cout * Cin;
+  const int64_t n = pairs * taps;
+  for (int64_t pr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pr < pairs; pr += (int64_t)gridDim.x * blockDim.x) {
+    for (int t = 0; t < taps; ++t) {
+      float s = 0.f;
+      for (int k = 0; k < splits; ++k) s += partial[(int64_t)k * n + (int64_t)t * pairs + pr];
+      dw[pr * taps + t] = s;
+    }
   }
 }
 
@@ -421,7 +423,7 @@ int bbdm_conv_wgrad(const void* g_hi_t, const void* g_lo_t, const void* a_hi, co
   else if (BN == 128) rc = launch_wgrad<128>(maps, p, grid, s);
   else rc = launch_wgrad<64>(maps, p, grid, s);
   if (rc) return rc;
-  const int64_t n = (int64_t)taps * Cout * Cin;
+  const int64_t n = (int64_t)Cout * Cin;
   int64_t g = (n + 255) / 256;
   if (g > (int64_t)num_sms() * 8) g = (int64_t)num_sms() * 8;
   wgrad_reduce_kernel<<<(int)g, 256, 0, s>>>(workspace, p.splits, taps, Cout, Cin, dw);

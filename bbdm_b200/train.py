@@ -126,7 +126,7 @@ class GNActConv2dFn(torch.autograd.Function):
     stats + prep + tcgen05 conv; the backward adds the two-pass GroupNorm/SiLU/FiLM gradient kernels."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale, shift, weight, bias, resample=0):
+    def forward(ctx, x, gamma, beta, scale, shift, weight, bias, resample=0, residual=None):
         """resample: 0 none, 1 nearest-2x up, 2 2x2 average pool -- applied between SiLU and the conv
         (ResBlock(up/down), openaimodel.py:259-264)."""
         be = backend()
@@ -151,12 +151,15 @@ class GNActConv2dFn(torch.autograd.Function):
         w_lo = torch.empty_like(w_hi)
         be.pack_weight_split(weight.detach().contiguous(), w_hi, w_lo)
         out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=dev)
+        rn = None if residual is None else _nhwc(residual.detach())       # + skip(x), fused in the epilogue
         be.conv_umma(B=B, H=H, W=W, Cin=Cin, Cout=Cout, taps=k * k, a_hi=a_hi, a_lo=a_lo, w_hi=w_hi, w_lo=w_lo,
-                     bias=None if bias is None else bias.detach(), out=out, passes=3)
+                     bias=None if bias is None else bias.detach(), residual=rn,
+                     res_mode=cabi.RES_NONE if rn is None else cabi.RES_SAME, out=out, passes=3)
         ctx.save_for_backward(xn, mean, rstd, gamma, beta, fs, fh, a_hi, a_lo, weight)
         ctx.has_bias = bias is not None
         ctx.shape = (B, H, W, Cin, Cout, k)
         ctx.resample = resample
+        ctx.has_res = residual is not None
         return out.permute(0, 3, 1, 2)
 
     @staticmethod
@@ -190,11 +193,12 @@ class GNActConv2dFn(torch.autograd.Function):
         s2 = (gf * a2).view(B, 32, Cin // 32).sum(2).contiguous()
         dxn = torch.empty((B, H, W, Cin), dtype=torch.float32, device=dev)
         be.gn_bwd_apply(xn, da, 32, mean, rstd, g, b_, fs, fh, fstride, True, s1, s2, dxn)
-        return dxn.permute(0, 3, 1, 2), dgamma, dbeta, dscale, dshift, dw, dbias, None
+        return dxn.permute(0, 3, 1, 2), dgamma, dbeta, dscale, dshift, dw, dbias, None, (dy if ctx.has_res else None)
 
 
-def gn_act_conv2d(norm, conv, x, scale=None, shift=None, enabled=True, resample=0):
-    """conv(resample(silu(norm(x) * (1 + scale) + shift))) -- fused tensor-core path when the shape qualifies."""
+def gn_act_conv2d(norm, conv, x, scale=None, shift=None, enabled=True, resample=0, residual=None):
+    """conv(resample(silu(norm(x) * (1 + scale) + shift))) [+ residual] -- fused tensor-core path when the
+    shape qualifies (the residual add then happens in the conv epilogue)."""
     B, _, Hs, Ws = x.shape
     H, W = (Hs * 2, Ws * 2) if resample == 1 else ((Hs // 2, Ws // 2) if resample == 2 else (Hs, Ws))
     probe = x if resample == 0 else x.new_empty((B, x.shape[1], H, W))       # shape check at the conv's resolution
@@ -202,7 +206,7 @@ def gn_act_conv2d(norm, conv, x, scale=None, shift=None, enabled=True, resample=
             (resample != 2 or (Hs % 2 == 0 and Ws % 2 == 0)):
         sc = None if scale is None else scale.reshape(scale.shape[0], -1)
         sh = None if shift is None else shift.reshape(shift.shape[0], -1)
-        return GNActConv2dFn.apply(x, norm.weight, norm.bias, sc, sh, conv.weight, conv.bias, resample)
+        return GNActConv2dFn.apply(x, norm.weight, norm.bias, sc, sh, conv.weight, conv.bias, resample, residual)
     h = norm(x)
     if scale is not None:
         h = h * (1 + scale) + shift
@@ -211,7 +215,8 @@ def gn_act_conv2d(norm, conv, x, scale=None, shift=None, enabled=True, resample=
         h = torch.nn.functional.interpolate(h, scale_factor=2, mode="nearest")
     elif resample == 2:
         h = torch.nn.functional.avg_pool2d(h, 2)
-    return conv2d(conv, h, enabled)
+    h = conv2d(conv, h, enabled)
+    return h if residual is None else residual + h
 
 
 class SmallConv2dFn(torch.autograd.Function):

@@ -134,9 +134,12 @@ class ResBlock(TimestepBlock):
         else:
             h = _gn_act_conv2d(self.in_layers[0], self.in_layers[2], x, None, None, nat)
         e = self.emb_layers(emb).type(h.dtype)[:, :, None, None]
+        skip_is_conv = isinstance(self.skip_connection, nn.Conv2d)
         if self.use_scale_shift_norm and self.dropout == 0:
             scale, shift = torch.chunk(e, 2, dim=1)
-            h = _gn_act_conv2d(self.out_layers[0], self.out_layers[3], h, scale, shift, nat)
+            # the skip path (identity or 1x1 conv of x) is added in the conv epilogue
+            sk = _conv2d(self.skip_connection, x, nat) if skip_is_conv else x
+            return _gn_act_conv2d(self.out_layers[0], self.out_layers[3], h, scale, shift, nat, residual=sk)
         else:
             if self.use_scale_shift_norm:
                 scale, shift = torch.chunk(e, 2, dim=1)

@@ -137,18 +137,23 @@ def test_gn_act_conv_function_gradients(B, H, W, C, Cout, film):
     shift = mk(0.3 * rnd((B, C), 14)) if film else None
     w, b = mk(rnd((Cout, C, 3, 3), 15, 0.05)), mk(rnd((Cout,), 16, 0.1))
     gy = rnd((B, Cout, H, W), 17, 0.2).to(DEV)
-    y = GNActConv2dFn.apply(x, gamma, beta, scale, shift, w, b)
+    res = mk(rnd((B, Cout, H, W), 18)) if film else None            # fused "+ skip" operand
+    y = GNActConv2dFn.apply(x, gamma, beta, scale, shift, w, b, 0, res)
     y.backward(gy)
 
     d = lambda t: None if t is None else t.detach().double().cpu().requires_grad_(True)
-    xd, gd, bd, sd, hd, wd, bbd = d(x), d(gamma), d(beta), d(scale), d(shift), d(w), d(b)
+    xd, gd, bd, sd, hd, wd, bbd, rd = d(x), d(gamma), d(beta), d(scale), d(shift), d(w), d(b), d(res)
     h = F.group_norm(xd, 32, gd, bd, 1e-5)
     if film:
         h = h * (1 + sd[:, :, None, None]) + hd[:, :, None, None]
     yd = F.conv2d(F.silu(h), wd, bbd, padding=1)
+    if res is not None:
+        yd = yd + rd
     yd.backward(gy.double().cpu())
     assert rel_dev(y, yd) < 3e-5
     pairs = [("x", x, xd), ("gamma", gamma, gd), ("beta", beta, bd), ("w", w, wd), ("b", b, bbd)]
+    if res is not None:
+        pairs.append(("residual", res, rd))
     if film:
         pairs += [("scale", scale, sd), ("shift", shift, hd)]
     for name, a, r in pairs:
