@@ -5,7 +5,10 @@
 //   * operands are the split-bf16 planes the qkv 1x1 conv wrote (qkv_hi/qkv_lo [B,T,3C]);
 //     TMA (3-D tiled maps, SWIZZLE_128B) stages Q once and K/V tiles through a 3-stage ring.
 //   * warp0 = TMA producer; warp1 = tcgen05.mma issuer (one lane) + TMEM owner;
-//     warps 2-5 = softmax / correction / epilogue, ONE QUERY ROW PER THREAD (no shuffles).
+//     warps 2-9 = TWO softmax / correction warpgroups, ONE QUERY ROW PER THREAD (no shuffles):
+//     group g owns the KV tiles j = g (mod 2) and the S/P/O buffers g, so the softmax of tile j+1
+//     runs concurrently with that of tile j (a single group left the tensor pipe 78 % idle); the
+//     two partial (max, sum, O) states are merged once at the end.
 //   * S_j = Q K_j^T      : M=128 x N=64 x K=64, A=Q (K-major), B=K_j (K-major)      -> TMEM S[j%2]
 //     O_j = P_j V_j      : M=128 x N=64 x K=64, A=P_j (K-major, written to smem by the softmax
 //                          warps in the UMMA swizzle), B=V_j as an MN-major operand      -> TMEM O[j%2]
@@ -47,7 +50,7 @@ struct AttnParams {
   unsigned long long* fault;
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                     const __grid_constant__ CUtensorMap map_kv_hi, const __grid_constant__ CUtensorMap map_kv_lo,
                     const AttnParams p) {
@@ -144,8 +147,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
       };
       mbar_wait(bar_q, 0, abort_flag, p.fault, 0xB0000000ull);
       issue_s(0);
+      if (n_tiles > 1) issue_s(1);
       for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) issue_s(j + 1);                // overlaps the softmax of tile j
         const int st = j % AT_STAGES, pbuf = j & 1, pu = j >> 1;
         mbar_wait(bar_pf + 8 * pbuf, pu & 1, abort_flag, p.fault, 0xB4000000ull | (unsigned)j);
         mbar_wait(bar_oe + 8 * pbuf, (pu & 1) ^ 1, abort_flag, p.fault, 0xB5000000ull | (unsigned)j);
@@ -166,11 +169,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         tc_commit(bar_of + 8 * pbuf);         // O_j ready
         tc_commit(bar_kve + 8 * st);          // K_j / V_j slot free
         tc_commit(bar_pe + 8 * pbuf);         // P buffer free
+        if (j + 2 < n_tiles) issue_s(j + 2);  // next tile of the same softmax group
       }
     }
     __syncwarp();
   } else {
     // ================================ softmax / correction / epilogue ===========================
+    const int grp = (warp - 2) >> 2;          // softmax group 0 / 1 <-> KV tiles of parity grp, buffers grp
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -196,79 +201,103 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
       if (lane == 0) mbar_arrive(bar_oe + 8 * obuf);
     };
 
-    for (int j = 0; j < n_tiles; ++j) {
+    for (int j = grp; j < n_tiles; j += 2) {
       const int sbuf = j & 1, su = j >> 1;
+      const int k0 = j * AT_BK;
       mbar_wait(bar_sf + 8 * sbuf, su & 1, abort_flag, p.fault, 0xB7000000ull | (unsigned)j);
       tc_fence_after();
-      float s[AT_BK];
-      {
-        uint32_t v[32];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          tc_ld32(lane_addr + sbuf * 64 + h * 32, v);
-          tc_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s[h * 32 + i] = __uint_as_float(v[i]) * p.scale_log2;
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_se + 8 * sbuf);          // S buffer may be overwritten
-
-      const int k0 = j * AT_BK;
+      // pass 1 over S_j (kept in TMEM, read twice to keep the register footprint small): row maximum
       float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < AT_BK; ++i) {
-        if (k0 + i >= p.T) s[i] = -INFINITY;
-        mx = fmaxf(mx, s[i]);
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tc_ld32(lane_addr + sbuf * 64 + h * 32, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (k0 + h * 32 + i < p.T) mx = fmaxf(mx, __uint_as_float(v[i]) * p.scale_log2);
       }
       const float m_new = fmaxf(m_run, mx);
       const float corr = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_new);
       m_run = m_new;
-      float rs = 0.f;
-#pragma unroll
-      for (int i = 0; i < AT_BK; ++i) { s[i] = ex2_approx(s[i] - m_new); rs += s[i]; }
-      l_run = l_run * corr + rs;
 
-      // ---- P_j -> shared memory in the UMMA K-major SWIZZLE_128B layout (row = query) ----------
+      // pass 2: P_j = 2^(S_j - m) -> shared memory in the UMMA K-major SWIZZLE_128B layout (row = query)
       const int pbuf = j & 1, pu = j >> 1;
       mbar_wait(bar_pe + 8 * pbuf, (pu & 1) ^ 1, abort_flag, p.fault, 0xB8000000ull | (unsigned)j);
-      {
-        const uint32_t ph = p_a + pbuf * 2 * AT_P_BYTES + row * 128, pl = ph + AT_P_BYTES;
+      const uint32_t ph = p_a + pbuf * 2 * AT_P_BYTES + row * 128, pl = ph + AT_P_BYTES;
+      float rs = 0.f;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {         // 16-byte chunk c = keys 8c..8c+7
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tc_ld32(lane_addr + sbuf * 64 + h * 32, v);
+        tc_wait_ld();
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          e[i] = (k0 + h * 32 + i < p.T) ? ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new)) : 0.f;
+          rs += e[i];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {           // 16-byte chunk (h*4 + c) = keys 8*(h*4+c) ..
           uint2 h0, l0, h1, l1;
-          split4(make_float4(s[8 * c], s[8 * c + 1], s[8 * c + 2], s[8 * c + 3]), h0, l0);
-          split4(make_float4(s[8 * c + 4], s[8 * c + 5], s[8 * c + 6], s[8 * c + 7]), h1, l1);
-          const uint32_t off = (uint32_t)((c ^ (row & 7)) * 16);
+          split4(make_float4(e[8 * c], e[8 * c + 1], e[8 * c + 2], e[8 * c + 3]), h0, l0);
+          split4(make_float4(e[8 * c + 4], e[8 * c + 5], e[8 * c + 6], e[8 * c + 7]), h1, l1);
+          const uint32_t off = (uint32_t)(((h * 4 + c) ^ (row & 7)) * 16);
           st_shared_v4(ph + off, h0.x, h0.y, h1.x, h1.y);
           st_shared_v4(pl + off, l0.x, l0.y, l1.x, l1.y);
         }
       }
+      l_run = l_run * corr + rs;
+      tc_fence_before();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_pf + 8 * pbuf);
+      if (lane == 0) { mbar_arrive(bar_se + 8 * sbuf); mbar_arrive(bar_pf + 8 * pbuf); }
 
-      // ---- fold the previous tile's P.V, then rescale to the new running max ----------------------
-      if (j > 0) fold_o(j - 1);
+      // fold this group's previous tile, then rescale to the new running max
+      if (j >= 2) fold_o(j - 2);
 #pragma unroll
       for (int i = 0; i < AT_D; ++i) o_reg[i] *= corr;
     }
-    fold_o(n_tiles - 1);
+    {
+      // last tile of this group (if it had any)
+      const int last = ((n_tiles - 1 - grp) >= 0) ? (n_tiles - 1 - ((n_tiles - 1 - grp) & 1)) : -1;
+      if (last >= grp) fold_o(last);
+    }
 
-    const int qr = q0 + row;
-    if (qr < p.T) {
-      const float inv = 1.0f / l_run;
-      const int64_t off = ((int64_t)b * p.T + qr) * p.C + head * AT_D;
+    // ---- merge the two groups' partial softmax states (group 1 -> shared memory -> group 0) ------------
+    // after the first barrier every MMA has completed (each group waited on its last O tile), so the
+    // K/V ring is no longer read by the tensor core and can carry the exchange
+    float* xch = reinterpret_cast<float*>(smem_raw + (kv_a - smem_u32(smem_raw)));
+    constexpr int XS = AT_D + 2;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (grp == 1) {
+      float* r = xch + row * XS;
+      r[0] = m_run; r[1] = l_run;
 #pragma unroll
-      for (int i = 0; i < AT_D; i += 4) {
-        const float4 v = make_float4(o_reg[i] * inv, o_reg[i + 1] * inv, o_reg[i + 2] * inv, o_reg[i + 3] * inv);
-        if (p.out_f32) st_f4(p.out_f32 + off + i, v);
-        if (p.out_hi) {
-          uint2 h, l;
-          split4(v, h, l);
-          *reinterpret_cast<uint2*>(p.out_hi + off + i) = h;
-          *reinterpret_cast<uint2*>(p.out_lo + off + i) = l;
+      for (int i = 0; i < AT_D; ++i) r[2 + i] = o_reg[i];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (grp == 0) {
+      const float* r = xch + row * XS;
+      const float m1 = r[0], l1 = r[1];
+      const float m = fmaxf(m_run, m1);
+      const float w0 = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m);
+      const float w1 = (m1 == -INFINITY) ? 0.f : ex2_approx(m1 - m);
+      const float inv = 1.0f / (l_run * w0 + l1 * w1);
+      const int qr = q0 + row;
+      if (qr < p.T) {
+        const int64_t off = ((int64_t)b * p.T + qr) * p.C + head * AT_D;
+#pragma unroll
+        for (int i = 0; i < AT_D; i += 4) {
+          const float4 v = make_float4((o_reg[i] * w0 + r[2 + i] * w1) * inv, (o_reg[i + 1] * w0 + r[3 + i] * w1) * inv,
+                                       (o_reg[i + 2] * w0 + r[4 + i] * w1) * inv, (o_reg[i + 3] * w0 + r[5 + i] * w1) * inv);
+          if (p.out_f32) st_f4(p.out_f32 + off + i, v);
+          if (p.out_hi) {
+            uint2 h, l;
+            split4(v, h, l);
+            *reinterpret_cast<uint2*>(p.out_hi + off + i) = h;
+            *reinterpret_cast<uint2*>(p.out_lo + off + i) = l;
+          }
         }
       }
     }
@@ -330,7 +359,7 @@ extern "C" int bbdm_attention_tc(const void* qkv_hi, const void* qkv_lo, int B, 
     configured = true;
   }
   dim3 grid((T + AT_BQ - 1) / AT_BQ, B * heads);
-  attention_tc_kernel<<<grid, 192, AT_SMEM, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], p);
+  attention_tc_kernel<<<grid, 320, AT_SMEM, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], p);
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
 }
