@@ -29,7 +29,7 @@ SYMBOLS = [
     "bbdm_pack_weight_f32", "bbdm_conv_umma", "bbdm_conv_direct",
     "bbdm_attention", "bbdm_attention_split", "bbdm_attention_tc", "bbdm_conv_umma_geometry", "bbdm_gn_finalize_partials",
     "bbdm_split_grad", "bbdm_conv_wgrad_workspace", "bbdm_conv_wgrad", "bbdm_gn_bwd_reduce", "bbdm_gn_bwd_apply",
-    "bbdm_conv_wgrad_direct",
+    "bbdm_conv_wgrad_direct", "bbdm_attention_bwd",
 ]
 
 
@@ -112,6 +112,7 @@ def load():
     lib.bbdm_gn_bwd_apply.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp, vp, i64, i, vp, vp, vp, vp]
     lib.bbdm_attention_split.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp]
     lib.bbdm_attention_tc.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp]
+    lib.bbdm_attention_bwd.argtypes = [vp, vp, vp, i, i, i, i, i, vp, vp, vp, vp]
     for s in SYMBOLS:
         fn = getattr(lib, s)
         if s not in ("bbdm_last_error",):
@@ -344,6 +345,12 @@ class CudaBackend:
         check(self.lib.bbdm_attention_tc(ptr(_req(qkv_hi, torch.bfloat16)), ptr(_req(qkv_lo, torch.bfloat16)),
                                          B, T, C3 // 3, heads, order, ptr(out_f32), ptr(out_hi), ptr(out_lo), stream()))
         LAUNCHES["n"] += 1
+
+    def attention_bwd(self, qkv, out, dout, heads, order, dqkv, lse, delta):
+        B, T, C3 = qkv.shape
+        check(self.lib.bbdm_attention_bwd(ptr(_req(qkv)), ptr(_req(out)), ptr(_req(dout)), B, T, C3 // 3, heads, order,
+                                          ptr(_req(dqkv)), ptr(_req(lse)), ptr(_req(delta)), stream()))
+        LAUNCHES["n"] += 2
 
     def check_fault(self):
         w = C.c_ulonglong(0)

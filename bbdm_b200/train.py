@@ -5,8 +5,8 @@ accumulation (fp32-class accuracy, like the reference's fp32 autograd).
 
 Tensors cross the Function boundary as ordinary NCHW-shaped torch tensors in channels_last
 memory format, i.e. physically the NHWC layout the kernels use: no layout copies when the
-surrounding ops keep channels_last.  GroupNorm / SiLU / attention / resampling stay on PyTorch
-autograd in this round (DESIGN.md "Training").
+surrounding ops keep channels_last.  GroupNorm+SiLU+FiLM(+resampling) in front of a conv and the
+attention core have their own Functions below (DESIGN.md "Training").
 
 Replaces the autograd of nn.Conv2d inside ResBlock (reference openaimodel.py:207,233,244) for
 ``loss.backward()`` (runners/BaseRunner.py:412); gradients land in the same nn.Parameter.grad, so
@@ -126,7 +126,7 @@ class GNActConv2dFn(torch.autograd.Function):
     stats + prep + tcgen05 conv; the backward adds the two-pass GroupNorm/SiLU/FiLM gradient kernels."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale, shift, weight, bias, resample=0, residual=None):
+    def forward(ctx, x, gamma, beta, scale, shift, weight, bias, resample=0, residual=None, act=True):
         """resample: 0 none, 1 nearest-2x up, 2 2x2 average pool -- applied between SiLU and the conv
         (ResBlock(up/down), openaimodel.py:259-264)."""
         be = backend()
@@ -145,7 +145,7 @@ class GNActConv2dFn(torch.autograd.Function):
         a_hi = torch.empty((B, H, W, Cin), dtype=torch.bfloat16, device=dev)
         a_lo = torch.empty_like(a_hi)
         be.prep(xn, None, groups=32, mean=mean, rstd=rstd, gamma=gamma.detach(), beta=beta.detach(), film_scale=fs,
-                film_shift=fh, film_stride=0 if fs is None else fs.shape[1], silu=True, resample=resample,
+                film_shift=fh, film_stride=0 if fs is None else fs.shape[1], silu=act, resample=resample,
                 act_hi=a_hi, act_lo=a_lo)
         w_hi = torch.empty((k * k, Cout, Cin), dtype=torch.bfloat16, device=dev)
         w_lo = torch.empty_like(w_hi)
@@ -160,6 +160,7 @@ class GNActConv2dFn(torch.autograd.Function):
         ctx.shape = (B, H, W, Cin, Cout, k)
         ctx.resample = resample
         ctx.has_res = residual is not None
+        ctx.act = act
         return out.permute(0, 3, 1, 2)
 
     @staticmethod
@@ -179,7 +180,7 @@ class GNActConv2dFn(torch.autograd.Function):
         fstride = 0 if fs is None else fs.shape[1]
         a12 = torch.empty((B, Cin, 2), dtype=torch.float32, device=dev)
         ws = torch.empty((B * 64 * Cin * 2,), dtype=torch.float32, device=dev)
-        be.gn_bwd_reduce(xn, da, 32, mean, rstd, g, b_, fs, fh, fstride, True, a12, ws)
+        be.gn_bwd_reduce(xn, da, 32, mean, rstd, g, b_, fs, fh, fstride, ctx.act, a12, ws)
         a1, a2 = a12[..., 0], a12[..., 1]                                  # [B, C]
         f1 = (1.0 + fs) if fs is not None else torch.ones_like(a1)
         dgamma = (f1 * a2).sum(0)
@@ -192,11 +193,11 @@ class GNActConv2dFn(torch.autograd.Function):
         s1 = (gf * a1).view(B, 32, Cin // 32).sum(2).contiguous()
         s2 = (gf * a2).view(B, 32, Cin // 32).sum(2).contiguous()
         dxn = torch.empty((B, H, W, Cin), dtype=torch.float32, device=dev)
-        be.gn_bwd_apply(xn, da, 32, mean, rstd, g, b_, fs, fh, fstride, True, s1, s2, dxn)
-        return dxn.permute(0, 3, 1, 2), dgamma, dbeta, dscale, dshift, dw, dbias, None, (dy if ctx.has_res else None)
+        be.gn_bwd_apply(xn, da, 32, mean, rstd, g, b_, fs, fh, fstride, ctx.act, s1, s2, dxn)
+        return dxn.permute(0, 3, 1, 2), dgamma, dbeta, dscale, dshift, dw, dbias, None, (dy if ctx.has_res else None), None
 
 
-def gn_act_conv2d(norm, conv, x, scale=None, shift=None, enabled=True, resample=0, residual=None):
+def gn_act_conv2d(norm, conv, x, scale=None, shift=None, enabled=True, resample=0, residual=None, act=True):
     """conv(resample(silu(norm(x) * (1 + scale) + shift))) [+ residual] -- fused tensor-core path when the
     shape qualifies (the residual add then happens in the conv epilogue)."""
     B, _, Hs, Ws = x.shape
@@ -206,11 +207,12 @@ def gn_act_conv2d(norm, conv, x, scale=None, shift=None, enabled=True, resample=
             (resample != 2 or (Hs % 2 == 0 and Ws % 2 == 0)):
         sc = None if scale is None else scale.reshape(scale.shape[0], -1)
         sh = None if shift is None else shift.reshape(shift.shape[0], -1)
-        return GNActConv2dFn.apply(x, norm.weight, norm.bias, sc, sh, conv.weight, conv.bias, resample, residual)
+        return GNActConv2dFn.apply(x, norm.weight, norm.bias, sc, sh, conv.weight, conv.bias, resample, residual, act)
     h = norm(x)
     if scale is not None:
         h = h * (1 + scale) + shift
-    h = torch.nn.functional.silu(h)
+    if act:
+        h = torch.nn.functional.silu(h)
     if resample == 1:
         h = torch.nn.functional.interpolate(h, scale_factor=2, mode="nearest")
     elif resample == 2:
@@ -285,6 +287,70 @@ def conv1x1(conv1d: torch.nn.Conv1d, x4: torch.Tensor, enabled: bool = True):
     if not ok:
         return None
     return Conv2dFn.apply(x4, conv1d.weight.unsqueeze(-1), conv1d.bias)
+
+
+class AttentionCoreFn(torch.autograd.Function):
+    """softmax((q s)(k s)^T) v per head (QKVAttentionLegacy / QKVAttention, openaimodel.py:350-413) on a
+    [B,3C,H,W] qkv tensor -> [B,C,H,W].  Forward: the sampling path's attention kernels (tcgen05 for
+    head_dim 64); backward: bbdm_attention_bwd (flash-style recompute, exact fp32) -- the T x T matrix is
+    never stored, which also replaces the reference's checkpoint() around the block (openaimodel.py:318)."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, order):
+        be = backend()
+        B, C3, H, W = qkv.shape
+        Cc, T = C3 // 3, H * W
+        dev = qkv.device
+        qn = _nhwc(qkv.detach()).contiguous()
+        out = torch.empty((B, T, Cc), dtype=torch.float32, device=dev)
+        if Cc // heads == 64:
+            q_hi = torch.empty((B, H, W, C3), dtype=torch.bfloat16, device=dev)
+            q_lo = torch.empty_like(q_hi)
+            be.prep(qn, None, raw_hi=q_hi, raw_lo=q_lo)
+            be.attention_tc(q_hi.view(B, T, C3), q_lo.view(B, T, C3), heads, order, out, None, None)
+        else:
+            be.attention(qn.view(B, T, C3), heads, order, out, None, None)
+        ctx.save_for_backward(qn, out)
+        ctx.heads, ctx.order = heads, order
+        return out.view(B, H, W, Cc).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dout):
+        be = backend()
+        qn, out = ctx.saved_tensors
+        B, H, W, C3 = qn.shape
+        T = H * W
+        dev = dout.device
+        don = _nhwc(dout).contiguous()
+        dqkv = torch.empty_like(qn)
+        lse = torch.empty((B * ctx.heads * T,), dtype=torch.float32, device=dev)
+        delta = torch.empty_like(lse)
+        be.attention_bwd(qn.view(B, T, C3), out, don.view(B, T, C3 // 3), ctx.heads, ctx.order,
+                         dqkv.view(B, T, C3), lse, delta)
+        return dqkv.permute(0, 3, 1, 2), None, None
+
+
+def attention_core(qkv4: torch.Tensor, heads: int, new_order: bool, enabled: bool = True):
+    """[B,3C,H,W] -> [B,C,H,W] or None when the native kernels do not take the shape."""
+    B, C3, H, W = qkv4.shape
+    hd = C3 // 3 // heads
+    if not (enabled and qkv4.is_cuda and qkv4.dtype == torch.float32 and hd in (16, 32, 64) and (C3 // 3) % 4 == 0
+            and B * heads <= 65535):
+        return None
+    return AttentionCoreFn.apply(qkv4, heads, 1 if new_order else 0)
+
+
+def gn_conv1x1(norm, conv1d: torch.nn.Conv1d, x4: torch.Tensor, enabled: bool = True):
+    """conv1d_k1(GroupNorm32(x)) of AttentionBlock (openaimodel.py:307,321) fused like gn_act_conv2d, without
+    the activation; None if the shape does not qualify."""
+    B, C, H, W = x4.shape
+    Cout = conv1d.out_channels
+    ok = (enabled and x4.is_cuda and x4.dtype == torch.float32 and conv1d.kernel_size == (1,) and C % 64 == 0
+          and Cout % 64 == 0 and W >= 4 and (B * H * W) % 64 == 0 and _box64_ok(B, H, W) and C <= 4096)
+    if not ok:
+        return None
+    return GNActConv2dFn.apply(x4, norm.weight, norm.bias, None, None, conv1d.weight.unsqueeze(-1), conv1d.bias,
+                               0, None, False)
 
 
 def conv2d(conv: torch.nn.Conv2d, x: torch.Tensor, enabled: bool = True) -> torch.Tensor:

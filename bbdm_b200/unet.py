@@ -24,7 +24,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .train import conv1x1 as _conv1x1, conv2d as _conv2d, gn_act_conv2d as _gn_act_conv2d
+from .train import (attention_core as _attention_core, conv1x1 as _conv1x1, conv2d as _conv2d,
+                    gn_act_conv2d as _gn_act_conv2d, gn_conv1x1 as _gn_conv1x1)
 
 # training path: ResBlock convolutions on the tcgen05 fwd / dgrad / wgrad kernels (bbdm_b200/train.py);
 # set False to run the whole training graph on stock PyTorch kernels
@@ -171,15 +172,30 @@ class AttentionBlock(nn.Module):
         self.proj_out = zero_module(nn.Conv1d(channels, channels, 1))
 
     def forward(self, x):
-        # (the reference wraps this in its CheckpointFunction, util.py:119-148: same values)
+        # Training forward.  The reference wraps this in its CheckpointFunction (util.py:119-148): same
+        # values; the native attention core never stores the T x T matrix, so nothing is recomputed.
         b, c, *spatial = x.shape
-        xf = x.reshape(b, c, -1)
-        qkv = None
-        if x.dim() == 4:          # qkv 1x1 on the tensor-core autograd path when the shape qualifies
-            q4 = _conv1x1(self.qkv, self.norm(x), NATIVE_TRAIN_CONV)
-            qkv = None if q4 is None else q4.reshape(b, 3 * c, -1)
-        if qkv is None:
-            qkv = self.qkv(self.norm(xf))
+        nat = NATIVE_TRAIN_CONV and x.dim() == 4
+        q4 = None
+        if nat:                   # GroupNorm + qkv 1x1 on the tensor-core autograd path when the shape qualifies
+            q4 = _gn_conv1x1(self.norm, self.qkv, x, True)
+            if q4 is None:
+                q4 = _conv1x1(self.qkv, self.norm(x), True)
+        a4 = _attention_core(q4, self.num_heads, self.new_order) if q4 is not None else None
+        if a4 is None:
+            xf = x.reshape(b, c, -1)
+            qkv = q4.reshape(b, 3 * c, -1) if q4 is not None else self.qkv(self.norm(xf))
+            a = self._attention_torch(qkv)
+            a4 = a.reshape(b, c, *spatial) if nat else None
+        if a4 is not None:
+            p4 = _conv1x1(self.proj_out, a4, True)
+            if p4 is not None:
+                return x + p4
+            a = a4.reshape(b, c, -1)
+        return (x.reshape(b, c, -1) + self.proj_out(a)).reshape(b, c, *spatial)
+
+    def _attention_torch(self, qkv):
+        """Stock-PyTorch attention core (CPU / shapes the native kernels do not take)."""
         bs, width, length = qkv.shape
         ch = width // (3 * self.num_heads)
         if self.new_order:
@@ -189,12 +205,7 @@ class AttentionBlock(nn.Module):
         scale = 1 / math.sqrt(math.sqrt(ch))
         w = torch.einsum("bct,bcs->bts", q * scale, k * scale)
         w = torch.softmax(w.float(), dim=-1).type(w.dtype)
-        a = torch.einsum("bts,bcs->bct", w, v).reshape(bs, -1, length)
-        if x.dim() == 4:
-            p4 = _conv1x1(self.proj_out, a.reshape(b, c, *spatial), NATIVE_TRAIN_CONV)
-            if p4 is not None:
-                return x + p4
-        return (xf + self.proj_out(a)).reshape(b, c, *spatial)
+        return torch.einsum("bts,bcs->bct", w, v).reshape(bs, -1, length)
 
 
 class UNetModel(nn.Module):

@@ -313,6 +313,14 @@ int bbdm_attention_split(const void* qkv_hi, const void* qkv_lo, int B, int T, i
 int bbdm_attention_tc(const void* qkv_hi, const void* qkv_lo, int B, int T, int C, int heads,
                       int order, float* out_f32, void* out_hi, void* out_lo, void* stream);
 
+/* Backward of the attention core (training; replaces the autograd + checkpoint() recompute of
+ * QKVAttentionLegacy / QKVAttention, openaimodel.py:318,350-413, util.py:119-148): given qkv [B,T,3C],
+ * out = attention(qkv) [B,T,C] and dout [B,T,C] (all fp32), writes dqkv [B,T,3C].  FlashAttention-style
+ * recompute in exact fp32 -- no T x T tensor.  lse, delta: fp32 workspaces of B*heads*T elements each.
+ * head_dim in {16,32,64}; deterministic. */
+int bbdm_attention_bwd(const float* qkv, const float* out, const float* dout, int B, int T, int C, int heads,
+                       int order, float* dqkv, float* lse, float* delta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
