@@ -29,7 +29,7 @@ SYMBOLS = [
     "bbdm_pack_weight_f32", "bbdm_conv_umma", "bbdm_conv_direct",
     "bbdm_attention", "bbdm_attention_split", "bbdm_attention_tc", "bbdm_conv_umma_geometry", "bbdm_gn_finalize_partials",
     "bbdm_split_grad", "bbdm_conv_wgrad_workspace", "bbdm_conv_wgrad", "bbdm_gn_bwd_reduce", "bbdm_gn_bwd_apply",
-    "bbdm_conv_wgrad_direct", "bbdm_attention_bwd",
+    "bbdm_conv_wgrad_direct", "bbdm_attention_bwd", "bbdm_conv_direct_pad", "bbdm_softmax_rows_split", "bbdm_vq_nearest",
 ]
 
 
@@ -113,6 +113,9 @@ def load():
     lib.bbdm_attention_split.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp]
     lib.bbdm_attention_tc.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp]
     lib.bbdm_attention_bwd.argtypes = [vp, vp, vp, i, i, i, i, i, vp, vp, vp, vp]
+    lib.bbdm_conv_direct_pad.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]
+    lib.bbdm_softmax_rows_split.argtypes = [vp, i64, i64, C.c_float, vp, vp, vp]
+    lib.bbdm_vq_nearest.argtypes = [vp, vp, i64, i, i, vp, vp, vp]
     for s in SYMBOLS:
         fn = getattr(lib, s)
         if s not in ("bbdm_last_error",):
@@ -351,6 +354,24 @@ class CudaBackend:
         check(self.lib.bbdm_attention_bwd(ptr(_req(qkv)), ptr(_req(out)), ptr(_req(dout)), B, T, C3 // 3, heads, order,
                                           ptr(_req(dqkv)), ptr(_req(lse)), ptr(_req(delta)), stream()))
         LAUNCHES["n"] += 2
+
+    def conv_direct_pad(self, src, w_packed, bias, residual, out, cout, k, stride, pad_lo, pad_hi):
+        B, H, W, Cin = src.shape
+        check(self.lib.bbdm_conv_direct_pad(ptr(_req(src)), ptr(_req(w_packed)), ptr(bias), ptr(residual), ptr(_req(out)),
+                                            B, H, W, Cin, cout, k, stride, pad_lo, pad_hi, stream()))
+        LAUNCHES["n"] += 1
+
+    def softmax_rows_split(self, src, scale, out_hi, out_lo):
+        rows, cols = src.numel() // src.shape[-1], src.shape[-1]
+        check(self.lib.bbdm_softmax_rows_split(ptr(_req(src)), rows, cols, float(scale), ptr(_req(out_hi, torch.bfloat16)),
+                                               ptr(_req(out_lo, torch.bfloat16)), stream()))
+        LAUNCHES["n"] += 1
+
+    def vq_nearest(self, z, codebook, z_q, indices):
+        n, d = z.numel() // z.shape[-1], z.shape[-1]
+        check(self.lib.bbdm_vq_nearest(ptr(_req(z)), ptr(_req(codebook)), n, codebook.shape[0], d, ptr(_req(z_q)),
+                                       ptr(_req(indices, torch.int64)), stream()))
+        LAUNCHES["n"] += 1
 
     def check_fault(self):
         w = C.c_ulonglong(0)

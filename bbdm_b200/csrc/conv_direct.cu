@@ -13,7 +13,7 @@ __global__ void __launch_bounds__(256)
 conv_direct_kernel(const float* __restrict__ src, const float* __restrict__ wp,
                    const float* __restrict__ bias, const float* __restrict__ res,
                    float* __restrict__ out, int B, int H, int W, int Cin, int Cout, int k,
-                   int stride, int Ho, int Wo) {
+                   int stride, int Ho, int Wo, int pad) {
   constexpr int TPN = TN / 4;          // threads along N (each 4 couts)
   constexpr int TPM = 256 / TPN;       // threads along M
   constexpr int PM = CD_TM / TPM;      // pixels per thread (TN=64: 4 ; TN=16: 1)
@@ -24,7 +24,6 @@ conv_direct_kernel(const float* __restrict__ src, const float* __restrict__ wp,
   const int64_t M = (int64_t)B * Ho * Wo;
   const int64_t m0 = (int64_t)blockIdx.x * CD_TM;
   const int n0 = blockIdx.y * TN;
-  const int pad = k / 2;
 
   // A-load assignment: 64 pixels x 16 cin = 1024 elements, 4 per thread
   const int a_p = tid / 4;             // pixel within tile
@@ -95,27 +94,41 @@ conv_direct_kernel(const float* __restrict__ src, const float* __restrict__ wp,
 
 using namespace bbdm;
 
-extern "C" int bbdm_conv_direct(const float* src, const float* w_packed, const float* bias,
-                                const float* residual, float* out, int B, int H, int W, int Cin,
-                                int Cout, int k, int stride, void* stream) {
+static int conv_direct_launch(const float* src, const float* w_packed, const float* bias, const float* residual,
+                              float* out, int B, int H, int W, int Cin, int Cout, int k, int stride, int pad_lo,
+                              int pad_hi, void* stream) {
   BBDM_REQUIRE(src && w_packed && out, "conv_direct: null pointer");
-  BBDM_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (k == 1 || k == 3) && (stride == 1 || stride == 2),
-               "conv_direct: bad shape");
-  const int pad = k / 2;
-  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  BBDM_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (k == 1 || k == 3) && (stride == 1 || stride == 2) &&
+               pad_lo >= 0 && pad_hi >= 0 && pad_lo < k && pad_hi < k, "conv_direct: bad shape");
+  BBDM_REQUIRE(H + pad_lo + pad_hi >= k && W + pad_lo + pad_hi >= k, "conv_direct: input smaller than the kernel");
+  const int Ho = (H + pad_lo + pad_hi - k) / stride + 1, Wo = (W + pad_lo + pad_hi - k) / stride + 1;
   const int64_t M = (int64_t)B * Ho * Wo;
   const int64_t gm = (M + CD_TM - 1) / CD_TM;
   BBDM_REQUIRE(gm < (1ll << 31), "conv_direct: too many pixels");
   cudaStream_t s = (cudaStream_t)stream;
   if (Cout <= 16) {
     dim3 grid((unsigned)gm, (Cout + 15) / 16);
-    conv_direct_kernel<16><<<grid, 256, 0, s>>>(src, w_packed, bias, residual, out, B, H, W, Cin, Cout, k, stride, Ho, Wo);
+    conv_direct_kernel<16><<<grid, 256, 0, s>>>(src, w_packed, bias, residual, out, B, H, W, Cin, Cout, k, stride, Ho, Wo, pad_lo);
   } else {
     dim3 grid((unsigned)gm, (Cout + 63) / 64);
-    conv_direct_kernel<64><<<grid, 256, 0, s>>>(src, w_packed, bias, residual, out, B, H, W, Cin, Cout, k, stride, Ho, Wo);
+    conv_direct_kernel<64><<<grid, 256, 0, s>>>(src, w_packed, bias, residual, out, B, H, W, Cin, Cout, k, stride, Ho, Wo, pad_lo);
   }
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
+}
+
+extern "C" int bbdm_conv_direct(const float* src, const float* w_packed, const float* bias,
+                                const float* residual, float* out, int B, int H, int W, int Cin,
+                                int Cout, int k, int stride, void* stream) {
+  return conv_direct_launch(src, w_packed, bias, residual, out, B, H, W, Cin, Cout, k, stride, k / 2, k / 2, stream);
+}
+
+// explicit zero padding: pad_lo rows/cols before, pad_hi after (VQGAN Downsample pads (0,1,0,1) and strides by
+// 2 with no further padding, model/VQGAN/model.py:55-73).  out: [B, Ho, Wo, Cout], Ho = (H+pad_lo+pad_hi-k)/stride+1
+extern "C" int bbdm_conv_direct_pad(const float* src, const float* w_packed, const float* bias,
+                                    const float* residual, float* out, int B, int H, int W, int Cin,
+                                    int Cout, int k, int stride, int pad_lo, int pad_hi, void* stream) {
+  return conv_direct_launch(src, w_packed, bias, residual, out, B, H, W, Cin, Cout, k, stride, pad_lo, pad_hi, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -60,20 +60,111 @@ class _Pool:
                 self.free.setdefault((tuple(t.shape), t.dtype), []).append(t)
 
 
-class UNetEngine:
-    def __init__(self, unet: UNetModel, backend=None, precision: str = "split3"):
-        self.unet = unet
+class KernelExecutor:
+    """What every executor over the C-ABI kernels shares: the backend, the precision mode, the buffer
+    pools, GroupNorm statistics (fused partials or a stats pass) and the convolution dispatch."""
+
+    gn_eps = GN_EPS
+
+    def __init__(self, backend=None, precision: str = "split3"):
         self.be = backend if backend is not None else cabi.CudaBackend()
         assert precision in ("split3", "bf16")
         self.passes = 3 if precision == "split3" else 1
         self.precision = precision
+        self._pools = {}
+        self._gn_ws = None
+        self._geom_cache = {}
+
+    def _umma_ok(self, cin, cout, w):
+        return cin % 64 == 0 and cout % 64 == 0 and w >= 4
+
+    # ------------------------------------------------------------------------------ helpers
+    def _pool(self, device, shape_key=None):
+        """Intermediate-buffer pool for one (device, input shape).  At most two shapes stay resident (the
+        steady batch and e.g. a smaller last batch of sample_to_eval); older pools are dropped so a
+        long-lived model does not accumulate HBM across shape changes."""
+        key = (device, shape_key)
+        p = self._pools.pop(key, None)
+        if p is None:
+            p = _Pool(self.be, device)
+            while len(self._pools) >= 2:
+                self._pools.pop(next(iter(self._pools)))       # evict least recently used
+        self._pools[key] = p                                   # (re)insert as most recent
+        return p
+
+    def pool_serial(self, device, shape_key):
+        return self._pool(device, shape_key).serial
+
+    def pool_bytes(self):
+        return sum(p.bytes for p in self._pools.values())
+
+    def _stats(self, pool, src1, src2):
+        B = src1.shape[0]
+        mean, rstd = pool.get((B, GN_GROUPS)), pool.get((B, GN_GROUPS))
+        g1 = getattr(src1, "_gn", None)
+        g2 = None if src2 is None else getattr(src2, "_gn", None)
+        if g1 is not None and (src2 is None or g2 is not None):
+            # both tensors came out of the tensor-core conv: its epilogue already reduced them
+            self.be.gn_finalize_partials(g1[0], g1[1], None if g2 is None else g2[0], 0 if g2 is None else g2[1],
+                                         B, src1.shape[1] * src1.shape[2], GN_GROUPS, self.gn_eps, mean, rstd)
+            return mean, rstd
+        if self._gn_ws is None or self._gn_ws.numel() < B * GN_GROUPS * cabi.GN_MAX_SLICES * 2 \
+                or self._gn_ws.device != src1.device:
+            self._gn_ws = self.be.empty((B * GN_GROUPS * cabi.GN_MAX_SLICES * 2,), torch.float64, src1.device)
+        self.be.gn_stats(src1, src2, GN_GROUPS, self.gn_eps, mean, rstd, self._gn_ws)
+        return mean, rstd
+
+    def _conv(self, pool, ent, *, a_f32=None, a_hi=None, a_lo=None, shape, bias=None, residual=None,
+              res_mode=cabi.RES_NONE, second=None, out_split=False, want_f32=True, stride=1, out=None,
+              stats=False):
+        """One convolution.  shape = (B,H,W) of the INPUT; returns (out_f32, out_hi, out_lo)."""
+        B, H, W = shape
+        cout, cin, k = ent["cout"], ent["cin"], ent["k"]
+        bias = ent["bias"] if bias is None else bias
+        if a_hi is not None:
+            if out is None:
+                out = pool.get((B, H, W, cout)) if want_f32 else None
+            oh = ol = None
+            if out_split:
+                oh, ol = pool.get((B, H, W, cout), torch.bfloat16), pool.get((B, H, W, cout), torch.bfloat16)
+            kw = {}
+            if second is not None:
+                e2, r_hi, r_lo = second
+                kw = dict(Cin2=e2["cin"], a2_hi=r_hi, a2_lo=r_lo, w2_hi=e2["hi"], w2_lo=e2["lo"], bias2=e2["bias"])
+            part = None
+            if stats and out is not None:
+                rows = self._geom(H, W)
+                if rows:
+                    part = pool.get((B * rows, cout, 2))
+            self.be.conv_umma(B=B, H=H, W=W, Cin=cin, Cout=cout, taps=k * k, a_hi=a_hi, a_lo=a_lo,
+                              w_hi=ent["hi"], w_lo=ent["lo"], bias=bias, residual=residual, res_mode=res_mode,
+                              out=out, out_hi=oh, out_lo=ol, passes=self.passes, stats_partial=part, **kw)
+            if part is not None:
+                out._gn = (part, rows)
+            return out, oh, ol
+        assert second is None and res_mode in (cabi.RES_NONE, cabi.RES_SAME) and not out_split
+        Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+        if out is None:
+            out = pool.get((B, Ho, Wo, cout))
+        self.be.conv_direct(a_f32, ent["f32"], bias, residual, out, cout, k, stride)
+        return out, None, None
+
+    def _geom(self, H, W):
+        key = (H, W)
+        r = self._geom_cache.get(key)
+        if r is None:
+            r = self._geom_cache[key] = self.be.conv_geometry(H, W)[3]
+        return r
+
+
+class UNetEngine(KernelExecutor):
+    def __init__(self, unet: UNetModel, backend=None, precision: str = "split3"):
+        super().__init__(backend, precision)
+        self.unet = unet
         self._wkey = None
         self._w = {}
-        self._pools = {}
         self._table = None
-        self._gn_ws = None
         self.num_timesteps = 1000
-        self._geom_cache = {}
         self.attention_impl = "tcgen05"      # "mma.sync" selects bbdm_attention_split for head_dim 64 too
         self.generation = 0          # bumps whenever cache/parameter ADDRESSES change (graphs key on it)
 
@@ -84,9 +175,6 @@ class UNetEngine:
     @staticmethod
     def _ptrs(key):
         return None if key is None else tuple(k[0] for k in key)
-
-    def _umma_ok(self, cin, cout, w):
-        return cin % 64 == 0 and cout % 64 == 0 and w >= 4
 
     def refresh_weights(self, force=False):
         """(Re)derive the packed weight caches if any parameter changed (optimizer step, EMA
@@ -179,84 +267,6 @@ class UNetEngine:
             # host-built with the reference's own expression (util.py:151-171): indexing is exact
             tab = timestep_embedding(torch.arange(self.num_timesteps), u.model_channels)
             self._table = tab.to(dev).contiguous()
-
-    # ------------------------------------------------------------------------------ helpers
-    def _pool(self, device, shape_key=None):
-        """Intermediate-buffer pool for one (device, input shape).  At most two shapes stay resident (the
-        steady batch and e.g. a smaller last batch of sample_to_eval); older pools are dropped so a
-        long-lived model does not accumulate HBM across shape changes."""
-        key = (device, shape_key)
-        p = self._pools.pop(key, None)
-        if p is None:
-            p = _Pool(self.be, device)
-            while len(self._pools) >= 2:
-                self._pools.pop(next(iter(self._pools)))       # evict least recently used
-        self._pools[key] = p                                   # (re)insert as most recent
-        return p
-
-    def pool_serial(self, device, shape_key):
-        return self._pool(device, shape_key).serial
-
-    def pool_bytes(self):
-        return sum(p.bytes for p in self._pools.values())
-
-    def _stats(self, pool, src1, src2):
-        B = src1.shape[0]
-        mean, rstd = pool.get((B, GN_GROUPS)), pool.get((B, GN_GROUPS))
-        g1 = getattr(src1, "_gn", None)
-        g2 = None if src2 is None else getattr(src2, "_gn", None)
-        if g1 is not None and (src2 is None or g2 is not None):
-            # both tensors came out of the tensor-core conv: its epilogue already reduced them
-            self.be.gn_finalize_partials(g1[0], g1[1], None if g2 is None else g2[0], 0 if g2 is None else g2[1],
-                                         B, src1.shape[1] * src1.shape[2], GN_GROUPS, GN_EPS, mean, rstd)
-            return mean, rstd
-        if self._gn_ws is None or self._gn_ws.numel() < B * GN_GROUPS * cabi.GN_MAX_SLICES * 2 \
-                or self._gn_ws.device != src1.device:
-            self._gn_ws = self.be.empty((B * GN_GROUPS * cabi.GN_MAX_SLICES * 2,), torch.float64, src1.device)
-        self.be.gn_stats(src1, src2, GN_GROUPS, GN_EPS, mean, rstd, self._gn_ws)
-        return mean, rstd
-
-    def _conv(self, pool, ent, *, a_f32=None, a_hi=None, a_lo=None, shape, bias=None, residual=None,
-              res_mode=cabi.RES_NONE, second=None, out_split=False, want_f32=True, stride=1, out=None,
-              stats=False):
-        """One convolution.  shape = (B,H,W) of the INPUT; returns (out_f32, out_hi, out_lo)."""
-        B, H, W = shape
-        cout, cin, k = ent["cout"], ent["cin"], ent["k"]
-        bias = ent["bias"] if bias is None else bias
-        if a_hi is not None:
-            if out is None:
-                out = pool.get((B, H, W, cout)) if want_f32 else None
-            oh = ol = None
-            if out_split:
-                oh, ol = pool.get((B, H, W, cout), torch.bfloat16), pool.get((B, H, W, cout), torch.bfloat16)
-            kw = {}
-            if second is not None:
-                e2, r_hi, r_lo = second
-                kw = dict(Cin2=e2["cin"], a2_hi=r_hi, a2_lo=r_lo, w2_hi=e2["hi"], w2_lo=e2["lo"], bias2=e2["bias"])
-            part = None
-            if stats and out is not None:
-                rows = self._geom(H, W)
-                if rows:
-                    part = pool.get((B * rows, cout, 2))
-            self.be.conv_umma(B=B, H=H, W=W, Cin=cin, Cout=cout, taps=k * k, a_hi=a_hi, a_lo=a_lo,
-                              w_hi=ent["hi"], w_lo=ent["lo"], bias=bias, residual=residual, res_mode=res_mode,
-                              out=out, out_hi=oh, out_lo=ol, passes=self.passes, stats_partial=part, **kw)
-            if part is not None:
-                out._gn = (part, rows)
-            return out, oh, ol
-        assert second is None and res_mode in (cabi.RES_NONE, cabi.RES_SAME) and not out_split
-        Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
-        if out is None:
-            out = pool.get((B, Ho, Wo, cout))
-        self.be.conv_direct(a_f32, ent["f32"], bias, residual, out, cout, k, stride)
-        return out, None, None
-
-    def _geom(self, H, W):
-        key = (H, W)
-        r = self._geom_cache.get(key)
-        if r is None:
-            r = self._geom_cache[key] = self.be.conv_geometry(H, W)[3]
-        return r
 
     # ------------------------------------------------------------------------------ blocks
     def _resblock(self, pool, name, m: ResBlock, src1, src2, film):

@@ -236,6 +236,13 @@ int bbdm_conv_direct(const float* src, const float* w_packed, const float* bias,
                      const float* residual, float* out, int B, int H, int W, int Cin, int Cout,
                      int k, int stride, void* stream);
 
+/* The same kernel with explicit zero padding (pad_lo before, pad_hi after, each < k): the VQGAN
+ * Downsample pads (0,1,0,1) and strides by 2 (model/VQGAN/model.py:55-73).
+ * out [B,Ho,Wo,Cout] with Ho = (H + pad_lo + pad_hi - k)/stride + 1. */
+int bbdm_conv_direct_pad(const float* src, const float* w_packed, const float* bias,
+                         const float* residual, float* out, int B, int H, int W, int Cin, int Cout,
+                         int k, int stride, int pad_lo, int pad_hi, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Training: gradients of the tensor-core convolution
  *   data gradient   dX = conv(dY, W^T flipped)  -> bbdm_conv_umma with re-packed weights
@@ -320,6 +327,18 @@ int bbdm_attention_tc(const void* qkv_hi, const void* qkv_lo, int B, int T, int 
  * head_dim in {16,32,64}; deterministic. */
 int bbdm_attention_bwd(const float* qkv, const float* out, const float* dout, int B, int T, int C, int heads,
                        int order, float* dqkv, float* lse, float* delta, void* stream);
+
+/* ---- VQGAN ends of the latent models ---------------------------------------
+ * Row softmax of a [rows, cols] fp32 score matrix, p = softmax(scale * s), written as split-bf16 planes
+ * (A operand of the P.V GEMM of the single-head AttnBlock, model/VQGAN/model.py:168-183). cols % 4 == 0. */
+int bbdm_softmax_rows_split(const float* src, int64_t rows, int64_t cols, float scale, void* out_hi,
+                            void* out_lo, void* stream);
+
+/* VectorQuantizer2.forward (model/VQGAN/quantize.py:271-312): for every latent vector z [n_vectors, dim]
+ * (NHWC order) the index of the nearest codebook row, d = (|z|^2 + |e|^2) - 2 z.e in fp32, first minimum;
+ * z_q = z + (e - z) (forward value of the straight-through expression).  dim <= 16. */
+int bbdm_vq_nearest(const float* z, const float* codebook, int64_t n_vectors, int n_embed, int dim,
+                    float* z_q, long long* indices, void* stream);
 
 #ifdef __cplusplus
 }

@@ -450,3 +450,91 @@ def op_conv_split3(a_nhwc, w_oihw, bias=None, residual=None):
 def op_attention_nhwc(qkv_btc, heads, new_order=False):
     """qkv [B,T,3C] (channel order as produced by the qkv 1x1 conv) -> [B,T,C]."""
     return qkv_attention(qkv_btc.permute(0, 2, 1), heads, new_order).permute(0, 2, 1).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------
+# VQGAN ends of the latent models (SURVEY 8(f) rank 1): functional restatement on a state_dict.
+#   Encoder / Decoder  model/VQGAN/model.py:342-537 ; ResnetBlock :76-138 ; AttnBlock :140-192 ;
+#   Downsample :55-73 ; Upsample :38-53 ; VectorQuantizer2.forward  quantize.py:271-312 ;
+#   VQModel.decode  vqgan.py:75-78.
+# ---------------------------------------------------------------------------------------------------
+def _vq_gn(sd, p, x):
+    return F.group_norm(x, 32, sd[p + ".weight"], sd[p + ".bias"], eps=1e-6)
+
+
+def _vq_conv(sd, p, x, stride=1, padding=None):
+    w = sd[p + ".weight"]
+    return F.conv2d(x, w, sd[p + ".bias"], stride=stride, padding=w.shape[2] // 2 if padding is None else padding)
+
+
+def _vq_resnet(sd, p, x):
+    h = _vq_conv(sd, p + ".conv1", F.silu(_vq_gn(sd, p + ".norm1", x)))
+    h = _vq_conv(sd, p + ".conv2", F.silu(_vq_gn(sd, p + ".norm2", h)))
+    if p + ".nin_shortcut.weight" in sd:
+        x = _vq_conv(sd, p + ".nin_shortcut", x)
+    elif p + ".conv_shortcut.weight" in sd:
+        x = _vq_conv(sd, p + ".conv_shortcut", x)
+    return x + h
+
+
+def _vq_attn(sd, p, x):
+    b, c, hh, ww = x.shape
+    h = _vq_gn(sd, p + ".norm", x)
+    q = _vq_conv(sd, p + ".q", h).reshape(b, c, -1)
+    k = _vq_conv(sd, p + ".k", h).reshape(b, c, -1)
+    v = _vq_conv(sd, p + ".v", h).reshape(b, c, -1)
+    w = torch.softmax(torch.einsum("bct,bcs->bts", q, k) * (int(c) ** (-0.5)), dim=2)     # [b, query, key]
+    o = torch.einsum("bcs,bts->bct", v, w).reshape(b, c, hh, ww)
+    return x + _vq_conv(sd, p + ".proj_out", o)
+
+
+def _vq_mid(sd, p, h):
+    h = _vq_resnet(sd, p + ".block_1", h)
+    h = _vq_attn(sd, p + ".attn_1", h)
+    return _vq_resnet(sd, p + ".block_2", h)
+
+
+def vqgan_encode(sd, dd, x, quant_conv=True):
+    """encoder(x) [-> quant_conv]; dd = the ddconfig dict."""
+    n_res, nrb = len(dd["ch_mult"]), dd["num_res_blocks"]
+    h = _vq_conv(sd, "encoder.conv_in", x)
+    for i in range(n_res):
+        for j in range(nrb):
+            h = _vq_resnet(sd, f"encoder.down.{i}.block.{j}", h)
+            if f"encoder.down.{i}.attn.{j}.norm.weight" in sd:
+                h = _vq_attn(sd, f"encoder.down.{i}.attn.{j}", h)
+        if i != n_res - 1:
+            h = _vq_conv(sd, f"encoder.down.{i}.downsample.conv", F.pad(h, (0, 1, 0, 1)), stride=2, padding=0)
+    h = _vq_mid(sd, "encoder.mid", h)
+    h = _vq_conv(sd, "encoder.conv_out", F.silu(_vq_gn(sd, "encoder.norm_out", h)))
+    return _vq_conv(sd, "quant_conv", h) if quant_conv else h
+
+
+def vqgan_quantize(sd, z):
+    """(z_q NCHW, indices [B*H*W]): nearest codebook row, z + (e - z)."""
+    cb = sd["quantize.embedding.weight"]
+    zf = z.permute(0, 2, 3, 1).contiguous()
+    flat = zf.view(-1, cb.shape[1])
+    d = torch.sum(flat ** 2, dim=1, keepdim=True) + torch.sum(cb ** 2, dim=1) - 2 * flat @ cb.t()
+    idx = torch.argmin(d, dim=1)
+    zq = cb[idx].view(zf.shape)
+    zq = zf + (zq - zf)
+    return zq.permute(0, 3, 1, 2).contiguous(), idx
+
+
+def vqgan_decode(sd, dd, z, quant_conv_first=False):
+    """[quant_conv ->] quantize -> post_quant_conv -> decoder."""
+    n_res, nrb = len(dd["ch_mult"]), dd["num_res_blocks"]
+    if quant_conv_first:
+        z = _vq_conv(sd, "quant_conv", z)
+    zq, idx = vqgan_quantize(sd, z)
+    h = _vq_conv(sd, "decoder.conv_in", _vq_conv(sd, "post_quant_conv", zq))
+    h = _vq_mid(sd, "decoder.mid", h)
+    for i in reversed(range(n_res)):
+        for j in range(nrb + 1):
+            h = _vq_resnet(sd, f"decoder.up.{i}.block.{j}", h)
+            if f"decoder.up.{i}.attn.{j}.norm.weight" in sd:
+                h = _vq_attn(sd, f"decoder.up.{i}.attn.{j}", h)
+        if i != 0:
+            h = _vq_conv(sd, f"decoder.up.{i}.upsample.conv", F.interpolate(h, scale_factor=2.0, mode="nearest"))
+    return _vq_conv(sd, "decoder.conv_out", F.silu(_vq_gn(sd, "decoder.norm_out", h))), idx

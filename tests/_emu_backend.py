@@ -246,5 +246,35 @@ class EmuBackend:
         assert qkv_hi.shape[2] // 3 // heads == 64
         self.attention(self._planes(qkv_hi, qkv_lo), heads, order, out_f32, out_hi, out_lo)
 
+    # -- VQGAN ends ---------------------------------------------------------------------------------------
+    def conv_direct_pad(self, src, w_packed, bias, residual, out, cout, k, stride, pad_lo, pad_hi):
+        self.calls.append("conv_direct_pad")
+        assert not torch.isnan(src).any()
+        cin = src.shape[3]
+        w = w_packed.reshape(k, k, cin, cout).permute(3, 2, 0, 1)
+        x = F.pad(src.permute(0, 3, 1, 2), (pad_lo, pad_hi, pad_lo, pad_hi))
+        o = F.conv2d(x, w, bias, stride=stride, padding=0).permute(0, 2, 3, 1)
+        out.copy_(o if residual is None else o + residual)
+
+    def softmax_rows_split(self, src, scale, out_hi, out_lo):
+        self.calls.append("softmax_rows_split")
+        assert not torch.isnan(src).any()
+        self._write_split(torch.softmax(src.reshape(out_hi.shape) * scale, dim=-1), out_hi, out_lo)
+
+    def vq_nearest(self, z, codebook, z_q, indices):
+        self.calls.append("vq_nearest")
+        flat = z.reshape(-1, codebook.shape[1])
+        d = torch.sum(flat ** 2, dim=1, keepdim=True) + torch.sum(codebook ** 2, dim=1) - 2 * flat @ codebook.t()
+        idx = torch.argmin(d, dim=1)
+        z_q.copy_((flat + (codebook[idx] - flat)).reshape(z_q.shape))
+        indices.copy_(idx.reshape(indices.shape))
+
+    def split_grad(self, src, hi, lo, hi_t, lo_t, colsum=None, workspace=None):
+        self.calls.append("split_grad")
+        h, l = O.bf16_split(src.float())
+        for dst, v in ((hi, h), (lo, l), (hi_t, h.t()), (lo_t, l.t())):
+            if dst is not None:
+                dst.copy_(v.reshape(dst.shape).to(torch.bfloat16))
+
     def check_fault(self):
         pass

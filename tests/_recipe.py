@@ -114,3 +114,30 @@ def rel_dev(a: torch.Tensor, b: torch.Tensor) -> float:
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ---- VQGAN ends: shrunken ddconfigs of Template-LBBDM-f*.yaml ---------------------------
+VQGAN_CONFIGS = {
+    # tensor-core paths: fused nin_shortcut, GEMM-composed AttnBlock (C=128, T=256), fused upsample conv, padded head
+    "vq_tc": dict(embed_dim=3, n_embed=128,
+                  ddconfig=dict(double_z=False, z_channels=3, resolution=32, in_channels=3, out_ch=3, ch=64,
+                                ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=[], dropout=0.0)),
+    # CUDA-core conv paths (C=32), flash AttnBlocks (C=64) inside a level, separate shortcut conv, z_channels 4
+    "vq_small": dict(embed_dim=4, n_embed=64,
+                     ddconfig=dict(double_z=False, z_channels=4, resolution=32, in_channels=3, out_ch=3, ch=32,
+                                   ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=[16], dropout=0.0)),
+}
+
+
+def vqgan_namespace(cfg: dict):
+    return dict(embed_dim=cfg["embed_dim"], n_embed=cfg["n_embed"], ckpt_path=None,
+                ddconfig=argparse.Namespace(**cfg["ddconfig"]),
+                lossconfig=argparse.Namespace(target="torch.nn.Identity"))
+
+
+def vqgan_state_dict(shapes: dict, seed: int = 4321):
+    """fill_state_dict + a codebook of O(1) entries (0.5 N(0,1), like a trained one) so that the nearest-code
+    search is well conditioned (the ctor's uniform(+-1/n_e) init puts every code within fp32 noise of the others)."""
+    sd = fill_state_dict(shapes, seed)
+    sd["quantize.embedding.weight"] = sd["quantize.embedding.weight"] * 25.0
+    return sd
