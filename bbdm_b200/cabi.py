@@ -29,7 +29,7 @@ SYMBOLS = [
     "bbdm_pack_weight_f32", "bbdm_conv_umma", "bbdm_conv_direct",
     "bbdm_attention", "bbdm_attention_split", "bbdm_attention_tc", "bbdm_conv_umma_geometry", "bbdm_gn_finalize_partials",
     "bbdm_split_grad", "bbdm_conv_wgrad_workspace", "bbdm_conv_wgrad", "bbdm_gn_bwd_reduce", "bbdm_gn_bwd_apply",
-    "bbdm_conv_wgrad_direct", "bbdm_attention_bwd", "bbdm_conv_direct_pad", "bbdm_softmax_rows_split", "bbdm_vq_nearest",
+    "bbdm_conv_wgrad_direct", "bbdm_attention_bwd", "bbdm_conv_direct_pad", "bbdm_softmax_rows_split", "bbdm_vq_nearest", "bbdm_s2d_split",
 ]
 
 
@@ -116,6 +116,7 @@ def load():
     lib.bbdm_conv_direct_pad.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]
     lib.bbdm_softmax_rows_split.argtypes = [vp, i64, i64, C.c_float, vp, vp, vp]
     lib.bbdm_vq_nearest.argtypes = [vp, vp, i64, i, i, vp, vp, vp]
+    lib.bbdm_s2d_split.argtypes = [vp, i, i, i, i, vp, vp, vp]
     for s in SYMBOLS:
         fn = getattr(lib, s)
         if s not in ("bbdm_last_error",):
@@ -365,6 +366,12 @@ class CudaBackend:
         rows, cols = src.numel() // src.shape[-1], src.shape[-1]
         check(self.lib.bbdm_softmax_rows_split(ptr(_req(src)), rows, cols, float(scale), ptr(_req(out_hi, torch.bfloat16)),
                                                ptr(_req(out_lo, torch.bfloat16)), stream()))
+        LAUNCHES["n"] += 1
+
+    def s2d_split(self, src, out_hi, out_lo):
+        B, H, W, Cc = src.shape
+        check(self.lib.bbdm_s2d_split(ptr(_req(src)), B, H, W, Cc, ptr(_req(out_hi, torch.bfloat16)),
+                                      ptr(_req(out_lo, torch.bfloat16)), stream()))
         LAUNCHES["n"] += 1
 
     def vq_nearest(self, z, codebook, z_q, indices):

@@ -171,6 +171,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               dx = (phase & 1) ? c : c - 1;
               wtap = phase * 4 + tap;
             } else if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+            else if (p.taps == 4) { dy = tap >> 1; dx = tap & 1; }   // 2x2 window at (0..1, 0..1): zero pad bottom/right
             tma_load_4d(sbase, &map_a_hi, full, cb * BK, w0 + dx, h0 + dy, b0);
             if (PASSES == 3) tma_load_4d(sbase + OFF_ALO, &map_a_lo, full, cb * BK, w0 + dx, h0 + dy, b0);
             tma_load_3d(sbase + OFF_WHI, &map_w_hi, full, cb * BK, n0, wtap);
@@ -460,7 +461,7 @@ extern "C" int bbdm_conv_umma_geometry(int H, int W, int* TW, int* TH, int* TB, 
 extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   BBDM_REQUIRE(a != nullptr, "conv_umma: null args");
   BBDM_REQUIRE(a->B > 0 && a->H > 0 && a->W > 0, "conv_umma: bad spatial shape");
-  BBDM_REQUIRE(a->taps == 1 || a->taps == 9 || (a->upsample2x && a->taps == 4), "conv_umma: taps must be 1 or 9 (got %d)", a->taps);
+  BBDM_REQUIRE(a->taps == 1 || a->taps == 9 || a->taps == 4, "conv_umma: taps must be 1, 4 or 9 (got %d)", a->taps);
   BBDM_REQUIRE(!a->upsample2x || (a->taps == 4 && a->Cin2 == 0), "conv_umma: upsample2x needs the 16 phase taps and no fused 1x1");
   BBDM_REQUIRE(a->Cin > 0 && a->Cin % 64 == 0, "conv_umma: Cin %% 64 != 0 (Cin=%d)", a->Cin);
   BBDM_REQUIRE(a->Cout > 0 && a->Cout % 64 == 0, "conv_umma: Cout %% 64 != 0 (Cout=%d)", a->Cout);

@@ -106,9 +106,43 @@ vq_nearest_kernel(const float* __restrict__ z, const float* __restrict__ cb, int
   }
 }
 
+// space-to-depth by 2 + bf16 split: dst[b, i, j, (a*2+b2)*C + c] = src[b, 2i+a, 2j+b2, c]
+__global__ void __launch_bounds__(256)
+s2d_split_kernel(const float* __restrict__ src, int64_t n4, int H, int W, int C, __nv_bfloat16* __restrict__ hi,
+                 __nv_bfloat16* __restrict__ lo) {
+  const int C4 = C / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int c = (int)(r % C4) * 4; r /= C4;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int64_t b = r / H;
+    const float4 v = ld_f4(src + i * 4);
+    uint2 ph, pl;
+    split4(v, ph, pl);
+    const int64_t o = (((b * (H / 2) + h / 2) * (W / 2) + w / 2) * 4 + (h & 1) * 2 + (w & 1)) * C + c;
+    *reinterpret_cast<uint2*>(hi + o) = ph;
+    *reinterpret_cast<uint2*>(lo + o) = pl;
+  }
+}
+
 }  // namespace bbdm
 
 using namespace bbdm;
+
+// [B,H,W,C] fp32 -> split-bf16 planes [B,H/2,W/2,4C] (channel = (row parity*2 + col parity)*C + c): the A operand
+// of a stride-2 3x3 convolution run as a 2x2-tap tensor-core conv (BbdmConvArgs.taps = 4).
+extern "C" int bbdm_s2d_split(const float* src, int B, int H, int W, int C, void* out_hi, void* out_lo, void* stream) {
+  BBDM_REQUIRE(src && out_hi && out_lo, "s2d_split: null pointer");
+  BBDM_REQUIRE(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 4 == 0, "s2d_split: bad shape");
+  const int64_t n4 = (int64_t)B * H * W * (C / 4);
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  s2d_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, n4, H, W, C, (__nv_bfloat16*)out_hi,
+                                                                       (__nv_bfloat16*)out_lo);
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
 
 extern "C" int bbdm_softmax_rows_split(const float* src, int64_t rows, int64_t cols, float scale, void* out_hi,
                                        void* out_lo, void* stream) {

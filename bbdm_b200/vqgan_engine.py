@@ -9,7 +9,8 @@ container, exactly like the UNet) and issues the same kernels as the UNet execut
                                   nin_shortcut rides as extra K-blocks of conv2, the identity skip as its residual
   AttnBlock   (model.py:140-192)  single head of width C: C <= 64 -> the flash kernels; C >= 128 -> per image two
                                   tensor-core GEMMs (S = Q K^T, O = P V) around bbdm_softmax_rows_split
-  Downsample  (model.py:55-73)    zero-pad (0,1,0,1) + stride-2 conv = bbdm_conv_direct_pad
+  Downsample  (model.py:55-73)    zero-pad (0,1,0,1) + stride-2 conv = space-to-depth split + 2x2-tap tcgen05 conv
+                                  (bbdm_conv_direct_pad for unaligned channel counts)
   Upsample    (model.py:38-53)    nearest-2x + conv3x3 = the fused 4-phase tcgen05 conv (no upsampled tensor)
   VectorQuantizer2 (quantize.py:271-312)  bbdm_vq_nearest
 
@@ -73,12 +74,30 @@ class VQGANEngine(KernelExecutor):
                 # q | k | v as one 1x1 conv ("new order" layout of the flash kernels, one head)
                 pack(name + ".qkv", torch.cat([m.q.weight, m.k.weight, m.v.weight], 0),
                      torch.cat([m.q.bias, m.k.bias, m.v.bias], 0))
+        for name, m in self.vq.named_modules():          # second pass: the convs above are packed now
             if type(m).__name__ == "Upsample" and m.with_conv and "hi" in w.get(name + ".conv", {}):
                 ent = w[name + ".conv"]
                 wp = upsample_phase_weights(m.conv.weight.detach())
                 ent["up_hi"] = be.empty((16, ent["cout"], ent["cin"]), torch.bfloat16, dev)
                 ent["up_lo"] = be.empty((16, ent["cout"], ent["cin"]), torch.bfloat16, dev)
                 be.pack_weight_split_taps(wp, ent["up_hi"], ent["up_lo"])
+            if type(m).__name__ == "Downsample" and m.with_conv:
+                # stride-2 3x3 conv on the zero-padded input == 2x2-tap conv over the space-to-depth tensor:
+                # W2[tap=(ty,tx)][co][(a*2+b)*C + ci] = w[co][ci][2ty+a][2tx+b]  (zero where 2ty+a or 2tx+b = 3)
+                cw = m.conv.weight.detach()
+                co, ci = cw.shape[0], cw.shape[1]
+                if co % 64 == 0 and (4 * ci) % 64 == 0:
+                    w2 = torch.zeros((co, 4, ci, 4), dtype=torch.float32, device=dev)     # [co][a*2+b][ci][tap]
+                    for ty in range(2):
+                        for tx in range(2):
+                            for a in range(2):
+                                for b in range(2):
+                                    if 2 * ty + a < 3 and 2 * tx + b < 3:
+                                        w2[:, a * 2 + b, :, ty * 2 + tx] = cw[:, :, 2 * ty + a, 2 * tx + b]
+                    ent = w[name + ".conv"]
+                    ent["ds_hi"] = be.empty((4, co, 4 * ci), torch.bfloat16, dev)
+                    ent["ds_lo"] = be.empty((4, co, 4 * ci), torch.bfloat16, dev)
+                    be.pack_weight_split_taps(w2.reshape(co, 4 * ci, 4).contiguous(), ent["ds_hi"], ent["ds_lo"])
         self._w, self._wkey = w, key
 
     # ------------------------------------------------------------------------------ pieces
@@ -195,6 +214,20 @@ class VQGANEngine(KernelExecutor):
         B, H, W, Cc = x.shape
         if m.with_conv:
             ent = self._w[name + ".conv"]
+            if "ds_hi" in ent and H % 2 == 0 and W % 2 == 0 and W // 2 >= 4:
+                hi = pool.get((B, H // 2, W // 2, 4 * Cc), torch.bfloat16)
+                lo = pool.get((B, H // 2, W // 2, 4 * Cc), torch.bfloat16)
+                self.be.s2d_split(x, hi, lo)
+                out = pool.get((B, H // 2, W // 2, Cc))
+                rows = self._geom(H // 2, W // 2)
+                part = pool.get((B * rows, Cc, 2)) if rows else None
+                self.be.conv_umma(B=B, H=H // 2, W=W // 2, Cin=4 * Cc, Cout=Cc, taps=4, a_hi=hi, a_lo=lo,
+                                  w_hi=ent["ds_hi"], w_lo=ent["ds_lo"], bias=ent["bias"], out=out, passes=self.passes,
+                                  stats_partial=part)
+                if part is not None:
+                    out._gn = (part, rows)
+                pool.put(hi, lo)
+                return out
             out = pool.get((B, (H + 1 - 3) // 2 + 1, (W + 1 - 3) // 2 + 1, Cc))
             self.be.conv_direct_pad(x, ent["f32"], ent["bias"], None, out, Cc, 3, 2, 0, 1)
             return out

@@ -182,7 +182,9 @@ enum { BBDM_RES_NONE = 0, BBDM_RES_SAME = 1, BBDM_RES_UP2 = 2, BBDM_RES_DOWN2 = 
  * TMA (4-D tiled maps, OOB zero fill = the conv padding), accumulate in TMEM (fp32).
  * passes = 3: A_hi.W_hi + A_lo.W_hi + A_hi.W_lo  (fp32-class accuracy, the parity mode)
  * passes = 1: A_hi.W_hi                           (plain bf16)
- * Requirements: Cin % 64 == 0, Cin2 % 64 == 0, Cout % 64 == 0, taps in {1, 9} (4 with upsample2x), W >= 4.
+ * Requirements: Cin % 64 == 0, Cin2 % 64 == 0, Cout % 64 == 0, taps in {1, 9}, or 4 (2x2 window at rows/cols (0..1), zero
+ * padding bottom/right -- the stride-2 conv on a space-to-depth operand, bbdm_s2d_split; with upsample2x the 4 taps
+ * are per output phase), W >= 4.
  * Replaces nn.Conv2d 3x3 / 1x1 in ResBlock (openaimodel.py:207,233,244), the qkv / proj_out
  * nn.Conv1d of AttentionBlock (:307,315) and the residual adds (:278,327). */
 typedef struct {
@@ -333,6 +335,12 @@ int bbdm_attention_bwd(const float* qkv, const float* out, const float* dout, in
  * (A operand of the P.V GEMM of the single-head AttnBlock, model/VQGAN/model.py:168-183). cols % 4 == 0. */
 int bbdm_softmax_rows_split(const float* src, int64_t rows, int64_t cols, float scale, void* out_hi,
                             void* out_lo, void* stream);
+
+/* Space-to-depth by 2 with bf16 split: src [B,H,W,C] fp32 -> planes [B,H/2,W/2,4C], channel
+ * (row parity*2 + col parity)*C + c.  With it the VQGAN Downsample (zero-pad (0,1,0,1) + 3x3 stride-2 conv,
+ * model/VQGAN/model.py:55-73) runs on the tensor cores as a 2x2-tap convolution over 4C channels
+ * (BbdmConvArgs.taps = 4: window rows/cols (0..1), zero padding at the bottom/right). H, W even; C % 4 == 0. */
+int bbdm_s2d_split(const float* src, int B, int H, int W, int C, void* out_hi, void* out_lo, void* stream);
 
 /* VectorQuantizer2.forward (model/VQGAN/quantize.py:271-312): for every latent vector z [n_vectors, dim]
  * (NHWC order) the index of the nearest codebook row, d = (|z|^2 + |e|^2) - 2 z.e in fp32, first minimum;

@@ -1,13 +1,16 @@
 """Drop-in ``LatentBrownianBridgeModel``: the latent-space wrapper around the B200-native
 bridge model.  Same surface as the reference class
 (/root/reference/model/BrownianBridge/LatentBrownianBridgeModel.py:19-132): frozen VQGAN
-encode/decode at both ends (kept as the reference's own PyTorch ``VQModel`` per the north star),
+encode/decode at both ends (kept as the reference's own PyTorch ``VQModel`` per the north star -- as the parameter container; on a GPU its encoder / quantiser / decoder run
+through ``bbdm_b200.vqgan_engine.VQGANEngine`` on the sm_100a kernels),
 optional cond-stage model, ``encode`` / ``decode`` / ``sample`` / ``sample_vqgan`` /
 ``get_ema_net`` and the latent mean/std attributes the runner assigns
 (BBDMRunner.py:41-44,136-158).  Everything between encode and decode -- q_sample, the UNet,
 the p_sample loop -- runs on the sm_100a kernels via the base class.
 """
 import itertools
+import os
+import warnings
 
 import torch
 
@@ -29,14 +32,17 @@ def _frozen_train(self, mode=True):
 def _load_vqmodel():
     try:
         from model.VQGAN.vqgan import VQModel   # the reference's module, unmodified
-    except ImportError as e:  # pragma: no cover - depends on deployment
-        raise ImportError(
-            "LatentBrownianBridgeModel needs the reference's frozen VQGAN (model.VQGAN.vqgan.VQModel): "
-            "put the BBDM checkout on sys.path behind this repo (see INTEGRATION.md)") from e
+    except ImportError:
+        # no BBDM checkout on sys.path: the repo's own parameter tree (same state_dict names); GPU only
+        from bbdm_b200.vqgan import VQModel
     return VQModel
 
 
 class LatentBrownianBridgeModel(BrownianBridgeModel):
+    # frozen autoencoder on the sm_100a kernels when the tensors live on a GPU (BBDM_NATIVE_VQGAN=0: keep the
+    # PyTorch module path)
+    native_vqgan = os.environ.get("BBDM_NATIVE_VQGAN", "1") != "0"
+
     def __init__(self, model_config):
         super().__init__(model_config)
         self.vqgan = _load_vqmodel()(**vars(model_config.VQGAN.params)).eval()
@@ -92,12 +98,35 @@ class LatentBrownianBridgeModel(BrownianBridgeModel):
             return self.cond_latent_mean, self.cond_latent_std
         return self.ori_latent_mean, self.ori_latent_std
 
+    def _vq_engine(self):
+        eng = self.__dict__.get("_vq_eng")
+        if eng is None:
+            from bbdm_b200.vqgan_engine import VQGANEngine
+            eng = self.__dict__["_vq_eng"] = VQGANEngine(self.vqgan)
+        return eng
+
+    def _native(self, fn, x, *args):
+        """Run the autoencoder end on the kernels; shapes they do not take fall back to the module (once warned)."""
+        if not (self.native_vqgan and x.is_cuda):
+            return None
+        try:
+            return fn(x, *args)
+        except NotImplementedError as e:
+            if not hasattr(self.vqgan.encoder, "forward") or type(self.vqgan).__module__.startswith("bbdm_b200"):
+                raise
+            warnings.warn(f"VQGAN on the PyTorch module path: {e}")
+            self.native_vqgan = False
+            return None
+
     @torch.no_grad()
     def encode(self, x, cond=True, normalize=None):
         normalize = self.model_config.normalize_latent if normalize is None else normalize
-        z = self.vqgan.encoder(x)
-        if not self.model_config.latent_before_quant_conv:
-            z = self.vqgan.quant_conv(z)
+        before = self.model_config.latent_before_quant_conv
+        z = self._native(lambda t: self._vq_engine().encode(t, quant_conv=not before), x)
+        if z is None:
+            z = self.vqgan.encoder(x)
+            if not before:
+                z = self.vqgan.quant_conv(z)
         if normalize:
             mean, std = self._norm_stats(cond)
             z = (z - mean) / std
@@ -109,7 +138,11 @@ class LatentBrownianBridgeModel(BrownianBridgeModel):
         if normalize:
             mean, std = self._norm_stats(cond)
             x_latent = x_latent * std + mean
-        if self.model_config.latent_before_quant_conv:
+        before = self.model_config.latent_before_quant_conv
+        out = self._native(lambda t: self._vq_engine().decode(t, quant_conv_first=before), x_latent)
+        if out is not None:
+            return out
+        if before:
             x_latent = self.vqgan.quant_conv(x_latent)
         x_latent_quant, _, _ = self.vqgan.quantize(x_latent)
         return self.vqgan.decode(x_latent_quant)

@@ -134,7 +134,12 @@ class EmuBackend:
         assert Cin % 64 == 0 and Cout % 64 == 0 and Cin2 % 64 == 0 and W >= 4
         a = self._planes(a_hi, a_lo).reshape(B, H, W, Cin)
         assert not torch.isnan(a).any()
-        o = O.op_conv_nhwc(a, self._oihw_from_split(w_hi, w_lo, taps), bias)
+        if taps == 4:
+            # 2x2 window at rows/cols (0..1), zero padding bottom/right
+            w4 = (w_hi.float() + w_lo.float()).reshape(2, 2, Cout, Cin).permute(2, 3, 0, 1)
+            o = F.conv2d(F.pad(a.permute(0, 3, 1, 2), (0, 1, 0, 1)), w4, bias).permute(0, 2, 3, 1)
+        else:
+            o = O.op_conv_nhwc(a, self._oihw_from_split(w_hi, w_lo, taps), bias)
         if Cin2:
             a2 = self._planes(a2_hi, a2_lo).reshape(B, H, W, Cin2)
             o = o + O.op_conv_nhwc(a2, self._oihw_from_split(w2_hi, w2_lo, 1), bias2)
@@ -260,6 +265,12 @@ class EmuBackend:
         self.calls.append("softmax_rows_split")
         assert not torch.isnan(src).any()
         self._write_split(torch.softmax(src.reshape(out_hi.shape) * scale, dim=-1), out_hi, out_lo)
+
+    def s2d_split(self, src, out_hi, out_lo):
+        self.calls.append("s2d_split")
+        B, H, W, Cc = src.shape
+        x = src.reshape(B, H // 2, 2, W // 2, 2, Cc).permute(0, 1, 3, 2, 4, 5).reshape(B, H // 2, W // 2, 4 * Cc)
+        self._write_split(x, out_hi, out_lo)
 
     def vq_nearest(self, z, codebook, z_q, indices):
         self.calls.append("vq_nearest")
