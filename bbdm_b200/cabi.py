@@ -29,7 +29,7 @@ SYMBOLS = [
     "bbdm_pack_weight_f32", "bbdm_conv_umma", "bbdm_conv_direct",
     "bbdm_attention", "bbdm_attention_split", "bbdm_attention_tc", "bbdm_conv_umma_geometry", "bbdm_gn_finalize_partials",
     "bbdm_split_grad", "bbdm_conv_wgrad_workspace", "bbdm_conv_wgrad", "bbdm_gn_bwd_reduce", "bbdm_gn_bwd_apply",
-    "bbdm_conv_wgrad_direct", "bbdm_attention_bwd", "bbdm_conv_direct_pad", "bbdm_softmax_rows_split", "bbdm_vq_nearest", "bbdm_s2d_split",
+    "bbdm_conv_wgrad_direct", "bbdm_attention_bwd", "bbdm_conv_direct_pad", "bbdm_softmax_rows_split", "bbdm_vq_nearest", "bbdm_s2d_split", "bbdm_pack_weight_split_both",
 ]
 
 
@@ -117,6 +117,7 @@ def load():
     lib.bbdm_softmax_rows_split.argtypes = [vp, i64, i64, C.c_float, vp, vp, vp]
     lib.bbdm_vq_nearest.argtypes = [vp, vp, i64, i, i, vp, vp, vp]
     lib.bbdm_s2d_split.argtypes = [vp, i, i, i, i, vp, vp, vp]
+    lib.bbdm_pack_weight_split_both.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp]
     for s in SYMBOLS:
         fn = getattr(lib, s)
         if s not in ("bbdm_last_error",):
@@ -249,6 +250,13 @@ class CudaBackend:
         """w [Cout,Cin,k,k] -> hi/lo [k*k, Cin, Cout] bf16: flipped kernel, swapped channels."""
         Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
         check(self.lib.bbdm_pack_weight_split_dgrad(ptr(_req(w)), Cout, Cin, k, ptr(hi), ptr(lo), stream()))
+        LAUNCHES["n"] += 1
+
+    def pack_weight_split_both(self, w, f_hi, f_lo, d_hi=None, d_lo=None):
+        """forward planes [k*k, Cout, Cin] and (optionally) data-gradient planes [k*k, Cin, Cout] in one pass."""
+        Cout, Cin, k = w.shape[0], w.shape[1], w.shape[2]
+        check(self.lib.bbdm_pack_weight_split_both(ptr(_req(w)), Cout, Cin, k, ptr(f_hi), ptr(f_lo), ptr(d_hi), ptr(d_lo),
+                                                   stream()))
         LAUNCHES["n"] += 1
 
     def pack_weight_split_taps(self, w, hi, lo):

@@ -143,11 +143,12 @@ namespace bbdm {
 
 constexpr int WD_MAX_PAIRS = 4;
 
+template <int k>
 __global__ void __launch_bounds__(256)
 conv_wgrad_direct_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ part,
-                         int B, int H, int W, int Cin, int Cout, int k, int px_per_block) {
+                         int B, int H, int W, int Cin, int Cout, int px_per_block) {
   const int pairs = Cin * Cout;
-  const int pad = k / 2, taps = k * k;
+  constexpr int pad = k / 2, taps = k * k;
   float acc[WD_MAX_PAIRS][9];
 #pragma unroll
   for (int i = 0; i < WD_MAX_PAIRS; ++i)
@@ -156,26 +157,41 @@ conv_wgrad_direct_kernel(const float* __restrict__ dy, const float* __restrict__
   const int64_t P = (int64_t)B * H * W;
   const int64_t p0 = (int64_t)blockIdx.x * px_per_block;
   const int64_t p1 = p0 + px_per_block < P ? p0 + px_per_block : P;
+  // per-thread constants of its (co, ci) pairs; pixel coordinates advance incrementally (no div/mod per pixel)
+  int co_[WD_MAX_PAIRS], ci_[WD_MAX_PAIRS];
+#pragma unroll
+  for (int i = 0; i < WD_MAX_PAIRS; ++i) {
+    const int pr = threadIdx.x + i * 256;
+    co_[i] = pr < pairs ? pr / Cin : -1;
+    ci_[i] = pr < pairs ? pr % Cin : 0;
+  }
+  int w = (int)(p0 % W), h = (int)((p0 / W) % H);
+  const float* dyp = dy + p0 * Cout;
+  const float* xp = x + p0 * Cin;           // pixel p itself; neighbours are +-(W*Cin), +-Cin away inside the image
   for (int64_t p = p0; p < p1; ++p) {
-    const int w = (int)(p % W);
-    const int h = (int)((p / W) % H);
-    const int b = (int)(p / ((int64_t)W * H));
-    const float* dyp = dy + p * Cout;
+    bool okh[3], okw[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      okh[d] = (unsigned)(h + d - pad) < (unsigned)H;
+      okw[d] = (unsigned)(w + d - pad) < (unsigned)W;
+    }
 #pragma unroll
     for (int i = 0; i < WD_MAX_PAIRS; ++i) {
-      const int pr = threadIdx.x + i * 256;
-      if (pr >= pairs) continue;
-      const int co = pr / Cin, ci = pr % Cin;
-      const float g = dyp[co];
+      if (co_[i] < 0) continue;
+      const float g = dyp[co_[i]];
+      const float* xc = xp + ci_[i];
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
         if (t < taps) {
-          const int hh = h + t / k - pad, ww = w + t % k - pad;
-          if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-            acc[i][t] = fmaf(g, x[(((int64_t)b * H + hh) * W + ww) * Cin + ci], acc[i][t]);
+          constexpr int kk = k;
+          const int dh = t / kk, dw = t % kk;           // compile-time after unrolling
+          if (okh[dh] && okw[dw])
+            acc[i][t] = fmaf(g, xc[((int64_t)(dh - pad) * W + (dw - pad)) * Cin], acc[i][t]);
         }
       }
     }
+    dyp += Cout; xp += Cin;
+    if (++w == W) { w = 0; if (++h == H) h = 0; }
   }
   float* o = part + (int64_t)blockIdx.x * taps * pairs;
 #pragma unroll
@@ -224,7 +240,8 @@ extern "C" int bbdm_conv_wgrad_direct(const float* dy, const float* x, int B, in
   const int ppb = (int)((P + nblk - 1) / nblk);
   nblk = (P + ppb - 1) / ppb;
   cudaStream_t s = (cudaStream_t)stream;
-  bbdm::conv_wgrad_direct_kernel<<<(unsigned)nblk, 256, 0, s>>>(dy, x, workspace, B, H, W, Cin, Cout, k, ppb);
+  if (k == 3) bbdm::conv_wgrad_direct_kernel<3><<<(unsigned)nblk, 256, 0, s>>>(dy, x, workspace, B, H, W, Cin, Cout, ppb);
+  else bbdm::conv_wgrad_direct_kernel<1><<<(unsigned)nblk, 256, 0, s>>>(dy, x, workspace, B, H, W, Cin, Cout, ppb);
   BBDM_LAUNCH_CHECK();
   bbdm::wgrad_direct_reduce_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(workspace, (int)nblk, k * k, Cout, Cin, dw);
   BBDM_LAUNCH_CHECK();

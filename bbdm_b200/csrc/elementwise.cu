@@ -194,6 +194,64 @@ pack_weight_split_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, i
   }
 }
 
+// forward AND data-gradient layouts in one pass over OIHW (training re-packs every weight each step):
+//   fwd[tap][co][ci] = w[co][ci][tap]          dgrad[t'][ci][co] = w[co][ci][kk-1-t']
+// 32x32 (co, ci) tile staged in shared memory: coalesced reads of the contiguous [ci][tap] runs, coalesced
+// bf16x2 writes along ci (fwd) and along co (dgrad).
+template <int KK>
+__global__ void __launch_bounds__(256)
+pack_weight_split_both_kernel(const float* __restrict__ w, int Cout, int Cin,
+                              __nv_bfloat16* __restrict__ f_hi, __nv_bfloat16* __restrict__ f_lo,
+                              __nv_bfloat16* __restrict__ d_hi, __nv_bfloat16* __restrict__ d_lo) {
+  constexpr int LD = 32 * KK + 1;
+  __shared__ float t[32 * LD];
+  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  const int nci = min(32, Cin - ci0), nco = min(32, Cout - co0);
+  for (int e = threadIdx.x; e < 32 * 32 * KK; e += 256) {
+    const int r = e / (32 * KK), c = e % (32 * KK);
+    if (r < nco && c < nci * KK) t[r * LD + c] = w[((int64_t)(co0 + r) * Cin + ci0) * KK + c];
+  }
+  __syncthreads();
+  if (f_hi) {
+    for (int e = threadIdx.x; e < KK * 32 * 16; e += 256) {          // pairs along ci
+      const int cp = e % 16, r = (e / 16) % 32, tap = e / (16 * 32);
+      const int ci = cp * 2;
+      if (r >= nco || ci >= nci) continue;
+      const float a = t[r * LD + ci * KK + tap], b = (ci + 1 < nci) ? t[r * LD + (ci + 1) * KK + tap] : 0.f;
+      __nv_bfloat16 ah, al, bh, bl;
+      split_bf16(a, ah, al);
+      split_bf16(b, bh, bl);
+      const int64_t o = ((int64_t)tap * Cout + co0 + r) * Cin + ci0 + ci;
+      if (ci + 1 < nci && (o & 1) == 0) {
+        *reinterpret_cast<__nv_bfloat162*>(f_hi + o) = __nv_bfloat162(ah, bh);
+        *reinterpret_cast<__nv_bfloat162*>(f_lo + o) = __nv_bfloat162(al, bl);
+      } else {
+        f_hi[o] = ah; f_lo[o] = al;
+        if (ci + 1 < nci) { f_hi[o + 1] = bh; f_lo[o + 1] = bl; }
+      }
+    }
+  }
+  if (d_hi) {
+    for (int e = threadIdx.x; e < KK * 32 * 16; e += 256) {          // pairs along co
+      const int rp = e % 16, c = (e / 16) % 32, tap = e / (16 * 32);
+      const int r = rp * 2;
+      if (c >= nci || r >= nco) continue;
+      const float a = t[r * LD + c * KK + tap], b = (r + 1 < nco) ? t[(r + 1) * LD + c * KK + tap] : 0.f;
+      __nv_bfloat16 ah, al, bh, bl;
+      split_bf16(a, ah, al);
+      split_bf16(b, bh, bl);
+      const int64_t o = ((int64_t)(KK - 1 - tap) * Cin + ci0 + c) * Cout + co0 + r;
+      if (r + 1 < nco && (o & 1) == 0) {
+        *reinterpret_cast<__nv_bfloat162*>(d_hi + o) = __nv_bfloat162(ah, bh);
+        *reinterpret_cast<__nv_bfloat162*>(d_lo + o) = __nv_bfloat162(al, bl);
+      } else {
+        d_hi[o] = ah; d_lo[o] = al;
+        if (r + 1 < nco) { d_hi[o + 1] = bh; d_lo[o + 1] = bl; }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 pack_weight_f32_kernel(const float* __restrict__ w, int Cout, int Cin, int kk, float* __restrict__ out) {
   const int64_t n = (int64_t)kk * Cout * Cin;
@@ -347,6 +405,24 @@ int bbdm_pack_weight_split_dgrad(const float* w, int Cout, int Cin, int k, void*
   const int64_t n = (int64_t)k * k * Cout * Cin;
   pack_weight_split_dgrad_kernel<<<grid_for(n, 256, num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(
       w, Cout, Cin, k * k, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo);
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
+int bbdm_pack_weight_split_both(const float* w, int Cout, int Cin, int k, void* fwd_hi, void* fwd_lo, void* dgrad_hi,
+                                void* dgrad_lo, void* stream) {
+  BBDM_REQUIRE(w && Cout > 0 && Cin > 0 && (k == 1 || k == 3), "pack_weight_split_both: bad args");
+  BBDM_REQUIRE((fwd_hi != nullptr) == (fwd_lo != nullptr) && (dgrad_hi != nullptr) == (dgrad_lo != nullptr) &&
+               (fwd_hi || dgrad_hi), "pack_weight_split_both: give hi and lo of at least one layout");
+  const dim3 grid((Cin + 31) / 32, (Cout + 31) / 32);
+  BBDM_REQUIRE(grid.y <= 65535, "pack_weight_split_both: Cout too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (k == 3)
+    pack_weight_split_both_kernel<9><<<grid, 256, 0, s>>>(w, Cout, Cin, (__nv_bfloat16*)fwd_hi, (__nv_bfloat16*)fwd_lo,
+                                                         (__nv_bfloat16*)dgrad_hi, (__nv_bfloat16*)dgrad_lo);
+  else
+    pack_weight_split_both_kernel<1><<<grid, 256, 0, s>>>(w, Cout, Cin, (__nv_bfloat16*)fwd_hi, (__nv_bfloat16*)fwd_lo,
+                                                         (__nv_bfloat16*)dgrad_hi, (__nv_bfloat16*)dgrad_lo);
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
 }

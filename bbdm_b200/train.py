@@ -56,6 +56,21 @@ def _nhwc(x):
     return x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)
 
 
+def _pack_weights(be, weight, need_dgrad):
+    """(w_hi, w_lo, wd_hi, wd_lo): forward planes and, if the input needs a gradient, the data-gradient planes
+    (flipped kernel, channels swapped) from the same single pass over the weight."""
+    Cout, Cin, k, _ = weight.shape
+    dev = weight.device
+    w_hi = torch.empty((k * k, Cout, Cin), dtype=torch.bfloat16, device=dev)
+    w_lo = torch.empty_like(w_hi)
+    wd_hi = wd_lo = None
+    if need_dgrad:
+        wd_hi = torch.empty((k * k, Cin, Cout), dtype=torch.bfloat16, device=dev)
+        wd_lo = torch.empty_like(wd_hi)
+    be.pack_weight_split_both(weight.detach().contiguous(), w_hi, w_lo, wd_hi, wd_lo)
+    return w_hi, w_lo, wd_hi, wd_lo
+
+
 class Conv2dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -67,26 +82,25 @@ class Conv2dFn(torch.autograd.Function):
         a_hi = torch.empty((B, H, W, Cin), dtype=torch.bfloat16, device=dev)
         a_lo = torch.empty_like(a_hi)
         be.prep(xn, None, raw_hi=a_hi, raw_lo=a_lo)                      # operand split (one HBM pass)
-        w_hi = torch.empty((k * k, Cout, Cin), dtype=torch.bfloat16, device=dev)
-        w_lo = torch.empty_like(w_hi)
-        be.pack_weight_split(weight.detach().contiguous(), w_hi, w_lo)
+        w_hi, w_lo, wd_hi, wd_lo = _pack_weights(be, weight, ctx.needs_input_grad[0])
         out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=dev)
         be.conv_umma(B=B, H=H, W=W, Cin=Cin, Cout=Cout, taps=k * k, a_hi=a_hi, a_lo=a_lo, w_hi=w_hi, w_lo=w_lo,
                      bias=None if bias is None else bias.detach(), out=out, passes=3)
-        ctx.save_for_backward(a_hi, a_lo, weight)
+        ctx.save_for_backward(a_hi, a_lo, weight, wd_hi, wd_lo)
         ctx.has_bias = bias is not None
         ctx.shape = (B, H, W, Cin, Cout, k)
         return out.permute(0, 3, 1, 2)                                   # NCHW shape, channels_last strides
 
     @staticmethod
     def backward(ctx, dy):
-        a_hi, a_lo, weight = ctx.saved_tensors
+        a_hi, a_lo, weight, wd_hi, wd_lo = ctx.saved_tensors
         dxn, dw, dbias = _conv_backward(backend(), ctx.shape, a_hi, a_lo, weight, dy, ctx.needs_input_grad[0],
-                                        ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2])
+                                        ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2],
+                                        wd=(wd_hi, wd_lo))
         return (None if dxn is None else dxn.permute(0, 3, 1, 2)), dw, dbias
 
 
-def _conv_backward(be, ctx_shape, a_hi, a_lo, weight, dy, need_dx, need_dw, need_db):
+def _conv_backward(be, ctx_shape, a_hi, a_lo, weight, dy, need_dx, need_dw, need_db, wd=(None, None)):
     """Shared by both Functions: (dA or dX as NHWC fp32, dW, dbias) of the tensor-core conv."""
     B, H, W, Cin, Cout, k = ctx_shape
     dev = dy.device
@@ -106,9 +120,11 @@ def _conv_backward(be, ctx_shape, a_hi, a_lo, weight, dy, need_dx, need_dw, need
     dxn = None
     if need_dx:
         # data gradient = the same conv with the kernel flipped and Cin/Cout swapped
-        wd_hi = torch.empty((k * k, Cin, Cout), dtype=torch.bfloat16, device=dev)
-        wd_lo = torch.empty_like(wd_hi)
-        be.pack_weight_split_dgrad(weight.detach().contiguous(), wd_hi, wd_lo)
+        wd_hi, wd_lo = wd
+        if wd_hi is None:
+            wd_hi = torch.empty((k * k, Cin, Cout), dtype=torch.bfloat16, device=dev)
+            wd_lo = torch.empty_like(wd_hi)
+            be.pack_weight_split_dgrad(weight.detach().contiguous(), wd_hi, wd_lo)
         dxn = torch.empty((B, H, W, Cin), dtype=torch.float32, device=dev)
         be.conv_umma(B=B, H=H, W=W, Cin=Cout, Cout=Cin, taps=k * k, a_hi=g_hi, a_lo=g_lo, w_hi=wd_hi, w_lo=wd_lo,
                      out=dxn, passes=3)
@@ -147,15 +163,13 @@ class GNActConv2dFn(torch.autograd.Function):
         be.prep(xn, None, groups=32, mean=mean, rstd=rstd, gamma=gamma.detach(), beta=beta.detach(), film_scale=fs,
                 film_shift=fh, film_stride=0 if fs is None else fs.shape[1], silu=act, resample=resample,
                 act_hi=a_hi, act_lo=a_lo)
-        w_hi = torch.empty((k * k, Cout, Cin), dtype=torch.bfloat16, device=dev)
-        w_lo = torch.empty_like(w_hi)
-        be.pack_weight_split(weight.detach().contiguous(), w_hi, w_lo)
+        w_hi, w_lo, wd_hi, wd_lo = _pack_weights(be, weight, True)
         out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=dev)
         rn = None if residual is None else _nhwc(residual.detach())       # + skip(x), fused in the epilogue
         be.conv_umma(B=B, H=H, W=W, Cin=Cin, Cout=Cout, taps=k * k, a_hi=a_hi, a_lo=a_lo, w_hi=w_hi, w_lo=w_lo,
                      bias=None if bias is None else bias.detach(), residual=rn,
                      res_mode=cabi.RES_NONE if rn is None else cabi.RES_SAME, out=out, passes=3)
-        ctx.save_for_backward(xn, mean, rstd, gamma, beta, fs, fh, a_hi, a_lo, weight)
+        ctx.save_for_backward(xn, mean, rstd, gamma, beta, fs, fh, a_hi, a_lo, weight, wd_hi, wd_lo)
         ctx.has_bias = bias is not None
         ctx.shape = (B, H, W, Cin, Cout, k)
         ctx.resample = resample
@@ -166,11 +180,11 @@ class GNActConv2dFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         be = backend()
-        xn, mean, rstd, gamma, beta, fs, fh, a_hi, a_lo, weight = ctx.saved_tensors
+        xn, mean, rstd, gamma, beta, fs, fh, a_hi, a_lo, weight, wd_hi, wd_lo = ctx.saved_tensors
         B, H, W, Cin, Cout, k = ctx.shape
         dev = dy.device
         da, dw, dbias = _conv_backward(be, ctx.shape, a_hi, a_lo, weight, dy, True, ctx.needs_input_grad[5],
-                                       ctx.has_bias and ctx.needs_input_grad[6])
+                                       ctx.has_bias and ctx.needs_input_grad[6], wd=(wd_hi, wd_lo))
         if ctx.resample == 1:        # adjoint of nearest-2x: sum the four children
             da = da.view(B, H // 2, 2, W // 2, 2, Cin).sum(dim=(2, 4)).contiguous()
         elif ctx.resample == 2:      # adjoint of the 2x2 mean: a quarter to each of the four parents

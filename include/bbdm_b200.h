@@ -170,6 +170,12 @@ int bbdm_pack_weight_split_taps(const float* w, int Cout, int Cin, int taps, voi
  * swapped, so that dX = bbdm_conv_umma(dY planes, these planes) (training backward). */
 int bbdm_pack_weight_split_dgrad(const float* w, int Cout, int Cin, int k, void* w_hi, void* w_lo,
                                  void* stream);
+
+/* Both layouts in ONE pass over the OIHW weight (the training step re-packs every weight after each optimizer
+ * update): fwd_* = bbdm_pack_weight_split's planes, dgrad_* = bbdm_pack_weight_split_dgrad's; either pair may be NULL.
+ * Shared-memory tiled transpose: coalesced reads and writes (the single-layout packers gather with a 36-byte stride). */
+int bbdm_pack_weight_split_both(const float* w, int Cout, int Cin, int k, void* fwd_hi, void* fwd_lo, void* dgrad_hi,
+                                void* dgrad_lo, void* stream);
 int bbdm_pack_weight_f32(const float* w, int Cout, int Cin, int k, float* out, void* stream);
 
 enum { BBDM_RES_NONE = 0, BBDM_RES_SAME = 1, BBDM_RES_UP2 = 2, BBDM_RES_DOWN2 = 3 };

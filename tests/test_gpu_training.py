@@ -284,3 +284,19 @@ def test_attention_block_training_matches_torch_graph():
     assert rel_dev(res[True][1], res[False][1]) < 1e-4
     for n in res[False][2]:
         assert rel_dev(res[True][2][n], res[False][2][n]) < 1e-4, n
+
+
+@pytest.mark.parametrize("Cout,Cin,k", [(64, 64, 3), (128, 192, 3), (256, 64, 1), (96, 40, 3), (33, 65, 1)])
+def test_pack_weight_split_both_equals_single_layout_packers(be, Cout, Cin, k):
+    w = rnd((Cout, Cin, k, k), 50, 0.05).to(DEV)
+    mk = lambda *s: torch.full(s, 7.0, dtype=torch.bfloat16, device=DEV)
+    f_hi, f_lo, d_hi, d_lo = mk(k * k, Cout, Cin), mk(k * k, Cout, Cin), mk(k * k, Cin, Cout), mk(k * k, Cin, Cout)
+    r_hi, r_lo, s_hi, s_lo = mk(k * k, Cout, Cin), mk(k * k, Cout, Cin), mk(k * k, Cin, Cout), mk(k * k, Cin, Cout)
+    be.pack_weight_split_both(w, f_hi, f_lo, d_hi, d_lo)
+    be.pack_weight_split(w, r_hi, r_lo)
+    be.pack_weight_split_dgrad(w, s_hi, s_lo)
+    for a, b in ((f_hi, r_hi), (f_lo, r_lo), (d_hi, s_hi), (d_lo, s_lo)):
+        assert torch.equal(a, b)
+    g_hi, g_lo = mk(k * k, Cout, Cin), mk(k * k, Cout, Cin)
+    be.pack_weight_split_both(w, g_hi, g_lo)                 # forward layout only
+    assert torch.equal(g_hi, r_hi) and torch.equal(g_lo, r_lo)
