@@ -3,13 +3,16 @@
 //
 //   * one CTA = 128 queries of one (batch, head); KV tiles of 64 keys; head_dim D = 64.
 //   * operands are the split-bf16 planes the qkv 1x1 conv wrote (qkv_hi/qkv_lo [B,T,3C]);
-//     TMA (3-D tiled maps, SWIZZLE_128B) stages Q once and K/V tiles through a 3-stage ring.
+//     TMA (3-D tiled maps, SWIZZLE_128B) stages Q once and K/V tiles through a 4-stage ring.
 //   * warp0 = TMA producer; warp1 = tcgen05.mma issuer (one lane) + TMEM owner;
 //     warps 2-9 = TWO softmax / correction warpgroups, ONE QUERY ROW PER THREAD (no shuffles):
 //     group g owns the KV tiles j = g (mod 2) and the S/P/O buffers g, so the softmax of tile j+1
 //     runs concurrently with that of tile j (a single group left the tensor pipe 78 % idle); the
-//     two partial (max, sum, O) states are merged once at the end.
-//   * S_j = Q K_j^T      : M=128 x N=64 x K=64, A=Q (K-major), B=K_j (K-major)      -> TMEM S[j%2]
+//     two partial (max, sum, O) states are merged once at the end.  Three S accumulators are in flight
+//     (S_{j+3} is issued right behind P_j V_j), so a group never waits for its next scores: with two the
+//     issue order P_{j-2}V_{j-2} -> S_j put two MMA groups between a group's tiles (34 % of all stall
+//     samples sat in the s_full wait, tensor pipe 25 % active).
+//   * S_j = Q K_j^T      : M=128 x N=64 x K=64, A=Q (K-major), B=K_j (K-major)      -> TMEM S[j%3]
 //     O_j = P_j V_j      : M=128 x N=64 x K=64, A=P_j (K-major, written to smem by the softmax
 //                          warps in the UMMA swizzle), B=V_j as an MN-major operand      -> TMEM O[j%2]
 //     every product is split-bf16 x3 (lo.hi + hi.lo + hi.hi, fp32 accumulate).
@@ -24,7 +27,8 @@ namespace bbdm {
 constexpr int AT_D = 64;
 constexpr int AT_BQ = 128;                // queries per CTA
 constexpr int AT_BK = 64;                 // keys per tile
-constexpr int AT_STAGES = 3;
+constexpr int AT_STAGES = 4;
+constexpr int AT_SBUF = 3;                // S accumulators in flight: S_{j+3} is issued right after P_j V_j
 constexpr uint32_t AT_Q_BYTES = AT_BQ * AT_D * 2;     // 16 KiB per plane
 constexpr uint32_t AT_KV_BYTES = AT_BK * AT_D * 2;    // 8 KiB per plane tile
 constexpr uint32_t AT_P_BYTES = AT_BQ * AT_BK * 2;    // 16 KiB per plane
@@ -55,7 +59,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
                     const __grid_constant__ CUtensorMap map_kv_hi, const __grid_constant__ CUtensorMap map_kv_lo,
                     const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[1 + 2 * AT_STAGES + 8];
+  __shared__ __align__(8) uint64_t bars[1 + 2 * AT_STAGES + 2 * AT_SBUF + 4];
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
 
@@ -67,10 +71,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
   const uint32_t bar_q = smem_u32(&bars[0]);
   const uint32_t bar_kvf = smem_u32(&bars[1]);                        // [STAGES]
   const uint32_t bar_kve = smem_u32(&bars[1 + AT_STAGES]);            // [STAGES]
-  const uint32_t bar_sf = smem_u32(&bars[1 + 2 * AT_STAGES]);         // s_full[2]
-  const uint32_t bar_se = bar_sf + 16;                                // s_empty[2]
-  const uint32_t bar_pf = bar_sf + 32;                                // p_full[2]
-  const uint32_t bar_pe = bar_sf + 48;                                // p_empty[2]
+  const uint32_t bar_sf = smem_u32(&bars[1 + 2 * AT_STAGES]);         // s_full[AT_SBUF]
+  const uint32_t bar_se = bar_sf + 8 * AT_SBUF;                       // s_empty[AT_SBUF]
+  const uint32_t bar_pf = bar_se + 8 * AT_SBUF;                       // p_full[2]
+  const uint32_t bar_pe = bar_pf + 16;                                // p_empty[2]
   __shared__ __align__(8) uint64_t bars_o[4];
   const uint32_t bar_of = smem_u32(&bars_o[0]);                       // o_full[2]
   const uint32_t bar_oe = bar_of + 16;                                // o_empty[2]
@@ -80,15 +84,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     abort_s = 0;
     mbar_init(bar_q, 1);
     for (int i = 0; i < AT_STAGES; ++i) { mbar_init(bar_kvf + 8 * i, 1); mbar_init(bar_kve + 8 * i, 1); }
+    for (int i = 0; i < AT_SBUF; ++i) { mbar_init(bar_sf + 8 * i, 1); mbar_init(bar_se + 8 * i, 4); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_sf + 8 * i, 1); mbar_init(bar_se + 8 * i, 4);
       mbar_init(bar_pf + 8 * i, 4); mbar_init(bar_pe + 8 * i, 1);
       mbar_init(bar_of + 8 * i, 1); mbar_init(bar_oe + 8 * i, 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(256) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -129,7 +133,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
       constexpr uint32_t IDESC_PV = IDESC_S | (1u << 16);
       const uint64_t dq_hi = make_sw128_desc(q_hi_a), dq_lo = make_sw128_desc(q_lo_a);
       auto issue_s = [&](int j) {
-        const int st = j % AT_STAGES, u = j / AT_STAGES, sbuf = j & 1, su = j >> 1;
+        const int st = j % AT_STAGES, u = j / AT_STAGES, sbuf = j % AT_SBUF, su = j / AT_SBUF;
         mbar_wait(bar_kvf + 8 * st, u & 1, abort_flag, p.fault, 0xB2000000ull | (unsigned)j);
         mbar_wait(bar_se + 8 * sbuf, (su & 1) ^ 1, abort_flag, p.fault, 0xB3000000ull | (unsigned)j);
         tc_fence_after();
@@ -147,7 +151,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
       };
       mbar_wait(bar_q, 0, abort_flag, p.fault, 0xB0000000ull);
       issue_s(0);
-      if (n_tiles > 1) issue_s(1);
+      for (int j = 1; j < AT_SBUF && j < n_tiles; ++j) issue_s(j);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % AT_STAGES, pbuf = j & 1, pu = j >> 1;
         mbar_wait(bar_pf + 8 * pbuf, pu & 1, abort_flag, p.fault, 0xB4000000ull | (unsigned)j);
@@ -156,7 +160,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         const uint32_t sb = kv_a + st * AT_STAGE_BYTES;
         const uint32_t pb = p_a + pbuf * 2 * AT_P_BYTES;
         const uint64_t dp_hi = make_sw128_desc(pb), dp_lo = make_sw128_desc(pb + AT_P_BYTES);
-        const uint32_t d_tmem = tmem_base + 128 + pbuf * 64;
+        const uint32_t d_tmem = tmem_base + AT_SBUF * 64 + pbuf * 64;
 #pragma unroll
         for (int k = 0; k < AT_BK / 16; ++k) {
           const uint64_t ka = (uint64_t)(k * 32 >> 4);                  // A = P: +32 B per 16 keys (K-major)
@@ -169,7 +173,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         tc_commit(bar_of + 8 * pbuf);         // O_j ready
         tc_commit(bar_kve + 8 * st);          // K_j / V_j slot free
         tc_commit(bar_pe + 8 * pbuf);         // P buffer free
-        if (j + 2 < n_tiles) issue_s(j + 2);  // next tile of the same softmax group
+        if (j + AT_SBUF < n_tiles) issue_s(j + AT_SBUF);   // keeps S two-to-three tiles ahead of the softmax groups
       }
     }
     __syncwarp();
@@ -188,49 +192,52 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
       const int obuf = j & 1, ou = j >> 1;
       mbar_wait(bar_of + 8 * obuf, ou & 1, abort_flag, p.fault, 0xB6000000ull | (unsigned)j);
       tc_fence_after();
-      uint32_t v[32];
+      // both halves' TMEM loads overlap the adds of the other half (tcgen05.ld latency is several hundred cycles)
+      uint32_t va[32], vb[32];
+      tc_ld32(lane_addr + AT_SBUF * 64 + obuf * 64, va);
+      tc_wait_ld();
+      tc_ld32(lane_addr + AT_SBUF * 64 + obuf * 64 + 32, vb);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        tc_ld32(lane_addr + 128 + obuf * 64 + h * 32, v);
-        tc_wait_ld();
+      for (int i = 0; i < 32; ++i) o_reg[i] += __uint_as_float(va[i]);
+      tc_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o_reg[h * 32 + i] += __uint_as_float(v[i]);
-      }
+      for (int i = 0; i < 32; ++i) o_reg[32 + i] += __uint_as_float(vb[i]);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_oe + 8 * obuf);
     };
 
     for (int j = grp; j < n_tiles; j += 2) {
-      const int sbuf = j & 1, su = j >> 1;
+      const int sbuf = j % AT_SBUF, su = j / AT_SBUF;
       const int k0 = j * AT_BK;
       mbar_wait(bar_sf + 8 * sbuf, su & 1, abort_flag, p.fault, 0xB7000000ull | (unsigned)j);
       tc_fence_after();
-      // pass 1 over S_j (kept in TMEM, read twice to keep the register footprint small): row maximum
+      // S_j stays in TMEM and is read twice (row maximum, then exponentials) to keep the register footprint
+      // small; every load is issued one step ahead so its latency hides behind the arithmetic of the other half
+      uint32_t va[32], vb[32];
+      const uint32_t s_addr = lane_addr + sbuf * 64;
       float mx = -INFINITY;
+      tc_ld32(s_addr, va);
+      tc_wait_ld();
+      tc_ld32(s_addr + 32, vb);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        tc_ld32(lane_addr + sbuf * 64 + h * 32, v);
-        tc_wait_ld();
+      for (int i = 0; i < 32; ++i)
+        if (k0 + i < p.T) mx = fmaxf(mx, __uint_as_float(va[i]) * p.scale_log2);
+      tc_wait_ld();
+      tc_ld32(s_addr, va);                      // first half again, for the exponentials
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (k0 + h * 32 + i < p.T) mx = fmaxf(mx, __uint_as_float(v[i]) * p.scale_log2);
-      }
+      for (int i = 0; i < 32; ++i)
+        if (k0 + 32 + i < p.T) mx = fmaxf(mx, __uint_as_float(vb[i]) * p.scale_log2);
       const float m_new = fmaxf(m_run, mx);
       const float corr = (m_run == -INFINITY) ? 0.f : ex2_approx(m_run - m_new);
       m_run = m_new;
 
-      // pass 2: P_j = 2^(S_j - m) -> shared memory in the UMMA K-major SWIZZLE_128B layout (row = query)
+      // P_j = 2^(S_j - m) -> shared memory in the UMMA K-major SWIZZLE_128B layout (row = query)
       const int pbuf = j & 1, pu = j >> 1;
       mbar_wait(bar_pe + 8 * pbuf, (pu & 1) ^ 1, abort_flag, p.fault, 0xB8000000ull | (unsigned)j);
       const uint32_t ph = p_a + pbuf * 2 * AT_P_BYTES + row * 128, pl = ph + AT_P_BYTES;
       float rs = 0.f;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        tc_ld32(lane_addr + sbuf * 64 + h * 32, v);
-        tc_wait_ld();
+      auto emit_half = [&](uint32_t (&v)[32], int h) {
         float e[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -246,7 +253,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
           st_shared_v4(ph + off, h0.x, h0.y, h1.x, h1.y);
           st_shared_v4(pl + off, l0.x, l0.y, l1.x, l1.y);
         }
-      }
+      };
+      tc_wait_ld();
+      tc_ld32(s_addr + 32, vb);
+      emit_half(va, 0);
+      tc_wait_ld();
+      emit_half(vb, 1);
       l_run = l_run * corr + rs;
       tc_fence_before();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
@@ -307,7 +319,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }
 
