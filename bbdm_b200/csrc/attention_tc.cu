@@ -127,7 +127,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
     __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ==============================================
-    if (lane == 0) {
+    // The whole warp runs this loop in uniform control flow (waits, descriptor arithmetic -> uniform datapath);
+    // only the tcgen05.mma / commit instructions sit under the elected lane's predicate.  With the loop inside
+    // `if (lane == 0)` every descriptor went through vector registers and 5 R2UR per MMA: 447 instructions per KV
+    // tile on one lane, which -- not the tensor pipe (25 % active) -- set the tile period.
+    const bool leader = elect_one_sync();
+    {
       // D=f32, A=B=bf16, M=128, N=64; PV additionally: B is MN-major (bit 16)
       constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       constexpr uint32_t IDESC_PV = IDESC_S | (1u << 16);
@@ -140,14 +145,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         const uint32_t sb = kv_a + st * AT_STAGE_BYTES;
         const uint64_t dk_hi = make_sw128_desc(sb), dk_lo = make_sw128_desc(sb + AT_KV_BYTES);
         const uint32_t d_tmem = tmem_base + sbuf * 64;
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k) {
-          const uint64_t ko = (uint64_t)(k * 32 >> 4);
-          tc_mma_bf16(d_tmem, dq_lo + ko, dk_hi + ko, IDESC_S, k ? 1u : 0u);
-          tc_mma_bf16(d_tmem, dq_hi + ko, dk_lo + ko, IDESC_S, 1u);
-          tc_mma_bf16(d_tmem, dq_hi + ko, dk_hi + ko, IDESC_S, 1u);
+          for (int k = 0; k < AT_D / 16; ++k) {
+            const uint64_t ko = (uint64_t)(k * 32 >> 4);
+            tc_mma_bf16(d_tmem, dq_lo + ko, dk_hi + ko, IDESC_S, k ? 1u : 0u);
+            tc_mma_bf16(d_tmem, dq_hi + ko, dk_lo + ko, IDESC_S, 1u);
+            tc_mma_bf16(d_tmem, dq_hi + ko, dk_hi + ko, IDESC_S, 1u);
+          }
+          tc_commit(bar_sf + 8 * sbuf);
         }
-        tc_commit(bar_sf + 8 * sbuf);
+        __syncwarp();
       };
       mbar_wait(bar_q, 0, abort_flag, p.fault, 0xB0000000ull);
       issue_s(0);
@@ -161,18 +169,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_c
         const uint32_t pb = p_a + pbuf * 2 * AT_P_BYTES;
         const uint64_t dp_hi = make_sw128_desc(pb), dp_lo = make_sw128_desc(pb + AT_P_BYTES);
         const uint32_t d_tmem = tmem_base + AT_SBUF * 64 + pbuf * 64;
+        const uint64_t dv0_hi = make_sw128_mn_desc(sb + 2 * AT_KV_BYTES), dv0_lo = make_sw128_mn_desc(sb + 3 * AT_KV_BYTES);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < AT_BK / 16; ++k) {
-          const uint64_t ka = (uint64_t)(k * 32 >> 4);                  // A = P: +32 B per 16 keys (K-major)
-          const uint32_t vb = sb + 2 * AT_KV_BYTES + k * 16 * 128;      // B = V: +16 key rows of 128 B (MN-major)
-          const uint64_t dv_hi = make_sw128_mn_desc(vb), dv_lo = make_sw128_mn_desc(vb + AT_KV_BYTES);
-          tc_mma_bf16(d_tmem, dp_lo + ka, dv_hi, IDESC_PV, k ? 1u : 0u);
-          tc_mma_bf16(d_tmem, dp_hi + ka, dv_lo, IDESC_PV, 1u);
-          tc_mma_bf16(d_tmem, dp_hi + ka, dv_hi, IDESC_PV, 1u);
+          for (int k = 0; k < AT_BK / 16; ++k) {
+            const uint64_t ka = (uint64_t)(k * 32 >> 4);                // A = P: +32 B per 16 keys (K-major)
+            const uint64_t kv = (uint64_t)(k * 16 * 128 >> 4);          // B = V: +16 key rows of 128 B (MN-major)
+            tc_mma_bf16(d_tmem, dp_lo + ka, dv0_hi + kv, IDESC_PV, k ? 1u : 0u);
+            tc_mma_bf16(d_tmem, dp_hi + ka, dv0_lo + kv, IDESC_PV, 1u);
+            tc_mma_bf16(d_tmem, dp_hi + ka, dv0_hi + kv, IDESC_PV, 1u);
+          }
+          tc_commit(bar_of + 8 * pbuf);         // O_j ready
+          tc_commit(bar_kve + 8 * st);          // K_j / V_j slot free
+          tc_commit(bar_pe + 8 * pbuf);         // P buffer free
         }
-        tc_commit(bar_of + 8 * pbuf);         // O_j ready
-        tc_commit(bar_kve + 8 * st);          // K_j / V_j slot free
-        tc_commit(bar_pe + 8 * pbuf);         // P buffer free
+        __syncwarp();
         if (j + AT_SBUF < n_tiles) issue_s(j + AT_SBUF);   // keeps S two-to-three tiles ahead of the softmax groups
       }
     }
