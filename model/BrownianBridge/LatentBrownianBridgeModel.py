@@ -165,5 +165,9 @@ class LatentBrownianBridgeModel(BrownianBridgeModel):
 
     @torch.no_grad()
     def sample_vqgan(self, x):
+        """Autoencoder round trip (reference :128-132: ``vqgan(x)`` = decode(quantize(quant_conv(encoder(x)))))."""
+        out = self._native(lambda t: self._vq_engine().decode(self._vq_engine().encode(t, quant_conv=True)), x)
+        if out is not None:
+            return out
         x_rec, _ = self.vqgan(x)
         return x_rec
