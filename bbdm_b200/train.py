@@ -28,9 +28,20 @@ def backend():
     return _BACKEND
 
 
+def set_backend(b):
+    """tests/ inject their oracle-backed emulation here to check this module's host logic (gradient formulas,
+    adjoints, tensor plumbing) on CPU; the product only ever uses cabi.CudaBackend."""
+    global _BACKEND
+    _BACKEND = b
+
+
+def _on_device(x: torch.Tensor) -> bool:
+    return x.is_cuda or (_BACKEND is not None and not getattr(_BACKEND, "requires_cuda", True))
+
+
 def native_ok(conv: torch.nn.Conv2d, x: torch.Tensor) -> bool:
     """Shapes the tensor-core fwd/dgrad/wgrad kernels take."""
-    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4:
+    if not _on_device(x) or x.dtype != torch.float32 or x.dim() != 4:
         return False
     k = conv.kernel_size
     B, _, H, W = x.shape
@@ -284,7 +295,7 @@ class SmallConv2dFn(torch.autograd.Function):
 
 def small_ok(conv: torch.nn.Conv2d, x: torch.Tensor) -> bool:
     k = conv.kernel_size
-    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and k in ((1, 1), (3, 3))
+    return (_on_device(x) and x.dtype == torch.float32 and x.dim() == 4 and k in ((1, 1), (3, 3))
             and conv.stride == (1, 1) and conv.padding == (k[0] // 2, k[0] // 2) and conv.groups == 1
             and conv.dilation == (1, 1) and conv.in_channels * conv.out_channels <= 1024
             and min(conv.in_channels, conv.out_channels) <= 32)
@@ -296,7 +307,7 @@ def conv1x1(conv1d: torch.nn.Conv1d, x4: torch.Tensor, enabled: bool = True):
     shape does not qualify (caller falls back to the module)."""
     B, C, H, W = x4.shape
     Cout = conv1d.out_channels
-    ok = (enabled and x4.is_cuda and x4.dtype == torch.float32 and conv1d.kernel_size == (1,) and C % 64 == 0
+    ok = (enabled and _on_device(x4) and x4.dtype == torch.float32 and conv1d.kernel_size == (1,) and C % 64 == 0
           and Cout % 64 == 0 and W >= 4 and (B * H * W) % 64 == 0 and _box64_ok(B, H, W))
     if not ok:
         return None
@@ -348,7 +359,7 @@ def attention_core(qkv4: torch.Tensor, heads: int, new_order: bool, enabled: boo
     """[B,3C,H,W] -> [B,C,H,W] or None when the native kernels do not take the shape."""
     B, C3, H, W = qkv4.shape
     hd = C3 // 3 // heads
-    if not (enabled and qkv4.is_cuda and qkv4.dtype == torch.float32 and hd in (16, 32, 64) and (C3 // 3) % 4 == 0
+    if not (enabled and _on_device(qkv4) and qkv4.dtype == torch.float32 and hd in (16, 32, 64) and (C3 // 3) % 4 == 0
             and B * heads <= 65535):
         return None
     return AttentionCoreFn.apply(qkv4, heads, 1 if new_order else 0)
@@ -359,7 +370,7 @@ def gn_conv1x1(norm, conv1d: torch.nn.Conv1d, x4: torch.Tensor, enabled: bool = 
     the activation; None if the shape does not qualify."""
     B, C, H, W = x4.shape
     Cout = conv1d.out_channels
-    ok = (enabled and x4.is_cuda and x4.dtype == torch.float32 and conv1d.kernel_size == (1,) and C % 64 == 0
+    ok = (enabled and _on_device(x4) and x4.dtype == torch.float32 and conv1d.kernel_size == (1,) and C % 64 == 0
           and Cout % 64 == 0 and W >= 4 and (B * H * W) % 64 == 0 and _box64_ok(B, H, W) and C <= 4096)
     if not ok:
         return None

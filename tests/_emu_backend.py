@@ -282,10 +282,82 @@ class EmuBackend:
 
     def split_grad(self, src, hi, lo, hi_t, lo_t, colsum=None, workspace=None):
         self.calls.append("split_grad")
-        h, l = O.bf16_split(src.float())
+        s2 = src.float().reshape(-1, src.shape[-1])
+        h, l = O.bf16_split(s2)
         for dst, v in ((hi, h), (lo, l), (hi_t, h.t()), (lo_t, l.t())):
             if dst is not None:
                 dst.copy_(v.reshape(dst.shape).to(torch.bfloat16))
+        if colsum is not None:
+            colsum.copy_(s2.double().sum(0).float())
+
+    # -- training gradients (host logic of bbdm_b200/train.py on CPU) ---------------------------------------
+    def pack_weight_split_dgrad(self, w, hi, lo):
+        self.calls.append("pack_weight_split_dgrad")
+        cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+        self._write_split(w.flip(2, 3).permute(2, 3, 1, 0).reshape(k * k, cin, cout), hi, lo)
+
+    def pack_weight_split_both(self, w, f_hi, f_lo, d_hi=None, d_lo=None):
+        self.calls.append("pack_weight_split_both")
+        if f_hi is not None:
+            self.pack_weight_split(w, f_hi, f_lo)
+        if d_hi is not None:
+            self.pack_weight_split_dgrad(w, d_hi, d_lo)
+
+    def wgrad_workspace(self, B, H, W, Cin, Cout, taps):
+        return 1, 1
+
+    @staticmethod
+    def _wgrad(a_nhwc, g_nhwc, k):
+        w = torch.zeros((g_nhwc.shape[3], a_nhwc.shape[3], k, k), dtype=torch.float64, requires_grad=True)
+        with torch.enable_grad():
+            F.conv2d(a_nhwc.double().permute(0, 3, 1, 2), w, padding=k // 2).backward(g_nhwc.double().permute(0, 3, 1, 2))
+        return w.grad.float()
+
+    def conv_wgrad(self, g_hi_t, g_lo_t, a_hi, a_lo, B, H, W, Cin, Cout, taps, dw, workspace):
+        self.calls.append("conv_wgrad")
+        g = self._planes(g_hi_t, g_lo_t).t().reshape(B, H, W, Cout)
+        dw.copy_(self._wgrad(self._planes(a_hi, a_lo).reshape(B, H, W, Cin), g, 3 if taps == 9 else 1))
+
+    def conv_wgrad_direct(self, dy, x, k, dw, workspace):
+        self.calls.append("conv_wgrad_direct")
+        dw.copy_(self._wgrad(x, dy, k))
+
+    @staticmethod
+    def _gn_bwd_terms(x, da, groups, mean, rstd, gamma, beta, fscale, fshift, silu):
+        B, H, W, C = x.shape
+        m = mean.repeat_interleave(C // groups, dim=1)[:, None, None, :]
+        r = rstd.repeat_interleave(C // groups, dim=1)[:, None, None, :]
+        xh = (x - m) * r
+        f1 = 1.0 if fscale is None else (1.0 + fscale[:, None, None, :C])
+        f0 = 0.0 if fscale is None else fshift[:, None, None, :C]
+        z = (gamma * xh + beta) * f1 + f0
+        if silu:
+            sg = torch.sigmoid(z)
+            dz = da * sg * (1 + z * (1 - sg))
+        else:
+            dz = da
+        return xh, dz, r, f1
+
+    def gn_bwd_reduce(self, x, da, groups, mean, rstd, gamma, beta, fscale, fshift, fstride, silu, a12, ws):
+        self.calls.append("gn_bwd_reduce")
+        xh, dz, _, _ = self._gn_bwd_terms(x, da, groups, mean, rstd, gamma, beta, fscale, fshift, silu)
+        a12[..., 0] = dz.double().sum((1, 2)).float()
+        a12[..., 1] = (dz * xh).double().sum((1, 2)).float()
+
+    def gn_bwd_apply(self, x, da, groups, mean, rstd, gamma, beta, fscale, fshift, fstride, silu, s1, s2, dx):
+        self.calls.append("gn_bwd_apply")
+        B, H, W, C = x.shape
+        xh, dz, r, f1 = self._gn_bwd_terms(x, da, groups, mean, rstd, gamma, beta, fscale, fshift, silu)
+        n = H * W * (C // groups)
+        e = lambda t: t.repeat_interleave(C // groups, dim=1)[:, None, None, :]
+        dx.copy_(r * (dz * gamma * f1 - (e(s1) + xh * e(s2)) / n))
+
+    def attention_bwd(self, qkv, out, dout, heads, order, dqkv, lse, delta):
+        self.calls.append("attention_bwd")
+        q = qkv.detach().double().requires_grad_(True)
+        with torch.enable_grad():
+            O.op_attention_nhwc(q, heads, bool(order)).backward(dout.double())
+        dqkv.copy_(q.grad.float())
 
     def check_fault(self):
         pass
