@@ -46,8 +46,9 @@ CONFIGS = {
                  batch=4, size=64, channels=3, sample_step=100,
                  name="pixel-BBDM 64x64 RGB, batch 4, 100 steps (BASELINE configs[0])",
                  flops_per_step=0.991e12),
-    # BASELINE configs[2..4]: the latent UNets (VQGAN ends excluded: the frozen reference module, out of
-    # the measured path).  These are parity-test cases; bench lines for them are informational.
+    # BASELINE configs[2..4]: the latent UNets (the step metric is the UNet's p_sample; the VQGAN ends run once per
+    # sampled batch and are timed separately, tools/bench_vqgan.py).  These are parity-test cases; bench lines for
+    # them are informational.
     "cfg3": dict(unet=dict(image_size=64, in_channels=3, model_channels=128, out_channels=3, num_res_blocks=2,
                            attention_resolutions=(32, 16, 8), channel_mult=(1, 4, 8), conv_resample=True, dims=2,
                            num_heads=8, num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True,
