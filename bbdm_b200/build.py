@@ -7,6 +7,7 @@ library has a plain C ABI (include/bbdm_b200.h) and is loaded with ctypes.
 from __future__ import annotations
 
 import os
+import shlex
 import subprocess
 import sys
 from concurrent.futures import ThreadPoolExecutor
@@ -18,6 +19,8 @@ SOURCES = ["cabi.cu", "elementwise.cu", "groupnorm.cu", "conv_direct.cu", "conv_
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+# opt-in experiment switches (e.g. BBDM_NVCC_DEFINES="-DBBDM_UNIFORM_ISSUE"); empty for the product build
+FLAGS += shlex.split(os.environ.get("BBDM_NVCC_DEFINES", ""))
 
 
 def _stale():

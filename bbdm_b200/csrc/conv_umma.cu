@@ -190,7 +190,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ============================================
+    // BBDM_UNIFORM_ISSUE (opt-in build flag, round-2 candidate, NOT yet validated on hardware for this kernel):
+    // the whole warp runs the loop in uniform control flow and only tcgen05.mma / commit sit under the elected
+    // lane's predicate, so ptxas keeps the descriptors in uniform registers.  The same change took the attention
+    // kernel from 5.8 to 4.0 ms; here it matters for the N = 64/128 tiles and the single-pass mode, where 12 (4)
+    // MMAs per K-block do not cover the ~250 issue-lane instructions spent on them (profiles/r01_ncu_attention_v6.md).
+#ifdef BBDM_UNIFORM_ISSUE
+    const bool leader = elect_one_sync();
+    {
+#else
+    const bool leader = true;
     if (lane == 0) {
+#endif
       // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
       constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                  ((uint32_t)(UM_BM >> 4) << 24);
@@ -212,22 +223,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             const uint64_t da_lo = make_kmajor_desc<BK>(sbase + OFF_ALO);
             const uint64_t db_hi = make_kmajor_desc<BK>(sbase + OFF_WHI);
             const uint64_t db_lo = make_kmajor_desc<BK>(sbase + OFF_WLO);
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 B per UMMA_K inside the swizzle atom
-              const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;   // a chunk starts from zero
-              if (PASSES == 3) {
-                tc_mma_bf16(d_tmem, da_lo + ko, db_hi + ko, IDESC, first);
-                tc_mma_bf16(d_tmem, da_hi + ko, db_lo + ko, IDESC, 1u);
-                tc_mma_bf16(d_tmem, da_hi + ko, db_hi + ko, IDESC, 1u);
-              } else {
-                tc_mma_bf16(d_tmem, da_hi + ko, db_hi + ko, IDESC, first);
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t ko = (uint64_t)(k * 32 >> 4);   // +32 B per UMMA_K inside the swizzle atom
+                const uint32_t first = (kb > kb0 || k > 0) ? 1u : 0u;   // a chunk starts from zero
+                if (PASSES == 3) {
+                  tc_mma_bf16(d_tmem, da_lo + ko, db_hi + ko, IDESC, first);
+                  tc_mma_bf16(d_tmem, da_hi + ko, db_lo + ko, IDESC, 1u);
+                  tc_mma_bf16(d_tmem, da_hi + ko, db_hi + ko, IDESC, 1u);
+                } else {
+                  tc_mma_bf16(d_tmem, da_hi + ko, db_hi + ko, IDESC, first);
+                }
               }
+              tc_commit(bar_empty + 8 * stage);        // frees the smem slot when these MMAs retire
             }
-            tc_commit(bar_empty + 8 * stage);          // frees the smem slot when these MMAs retire
+#ifdef BBDM_UNIFORM_ISSUE
+            __syncwarp();
+#endif
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(bar_tfull + 8 * acc);              // chunk complete -> promotion warps
+          if (leader) tc_commit(bar_tfull + 8 * acc);  // chunk complete -> promotion warps
+#ifdef BBDM_UNIFORM_ISSUE
+          __syncwarp();
+#endif
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
