@@ -126,7 +126,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
+    // BBDM_UNIFORM_ISSUE: opt-in warp-uniform MMA issue (see conv_umma.cu); the default build is unchanged
+#ifdef BBDM_UNIFORM_ISSUE
+    const bool leader = elect_one_sync();
+    {
+#else
+    const bool leader = true;
     if (lane == 0) {
+#endif
       // D=f32, A=B=bf16, A K-major, B MN-major (bit 16), N=BN, M=128
       constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
                                  ((uint32_t)(WG_BM >> 4) << 24);
@@ -146,20 +153,28 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_con
             tc_fence_after();
             const uint32_t sb = tiles_base + stage * STAGE_BYTES;
             const uint64_t dg_hi = make_sw128_desc(sb), dg_lo = make_sw128_desc(sb + G_BYTES);
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < WG_BK / 16; ++k) {
-              const uint64_t ka = (uint64_t)(k * 32 >> 4);                     // A: +32 B per 16 pixels (K-major)
-              const uint32_t ab = sb + 2 * G_BYTES + k * 16 * 128;              // B: +16 pixel rows of 128 B
-              const uint64_t da_hi = make_mn_desc(ab, A_ATOM), da_lo = make_mn_desc(ab + A_BYTES, A_ATOM);
-              const uint32_t first = (kb > c0 || k > 0) ? 1u : 0u;
-              tc_mma_bf16(d_tmem, dg_lo + ka, da_hi, IDESC, first);
-              tc_mma_bf16(d_tmem, dg_hi + ka, da_lo, IDESC, 1u);
-              tc_mma_bf16(d_tmem, dg_hi + ka, da_hi, IDESC, 1u);
+              for (int k = 0; k < WG_BK / 16; ++k) {
+                const uint64_t ka = (uint64_t)(k * 32 >> 4);                   // A: +32 B per 16 pixels (K-major)
+                const uint32_t ab = sb + 2 * G_BYTES + k * 16 * 128;            // B: +16 pixel rows of 128 B
+                const uint64_t da_hi = make_mn_desc(ab, A_ATOM), da_lo = make_mn_desc(ab + A_BYTES, A_ATOM);
+                const uint32_t first = (kb > c0 || k > 0) ? 1u : 0u;
+                tc_mma_bf16(d_tmem, dg_lo + ka, da_hi, IDESC, first);
+                tc_mma_bf16(d_tmem, dg_hi + ka, da_lo, IDESC, 1u);
+                tc_mma_bf16(d_tmem, dg_hi + ka, da_hi, IDESC, 1u);
+              }
+              tc_commit(bar_empty + 8 * stage);
             }
-            tc_commit(bar_empty + 8 * stage);
+#ifdef BBDM_UNIFORM_ISSUE
+            __syncwarp();
+#endif
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(bar_tfull + 8 * acc);
+          if (leader) tc_commit(bar_tfull + 8 * acc);
+#ifdef BBDM_UNIFORM_ISSUE
+          __syncwarp();
+#endif
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
