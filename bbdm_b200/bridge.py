@@ -107,7 +107,8 @@ class BridgeOps:
                 one_step_imgs.append(x0_recon)
             return imgs, one_step_imgs
         if self.use_cuda_graph and y.is_cuda and getattr(self.backend(), "requires_cuda", False):
-            return self._graphed_loop(y, context, clip_denoised, it)
+            with torch.cuda.device(y.device):         # capture/replay on the tensors' device, not the process default
+                return self._graphed_loop(y, context, clip_denoised, it)
         img = y
         for i in it:
             img, _ = self.p_sample(img, y, context, i, clip_denoised, _fresh=True)

@@ -12,7 +12,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbbdm_b200.so")
+# BBDM_LIB selects another in-tree build of the same sources (A/B experiments, tools/); the product default is fixed
+LIB_PATH = os.environ.get("BBDM_LIB") or os.path.join(_HERE, "libbbdm_b200.so")
 
 ABI_VERSION = 1
 OBJ = {"grad": 0, "noise": 1, "ysubx": 2}
@@ -139,7 +140,41 @@ def ptr(t):
 
 
 def stream():
+    """torch's current stream of the CURRENT device; CudaBackend methods make the tensors' device current first."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def _device_guarded(fn):
+    """Run a backend method with the device of its first CUDA tensor argument current.  The reference's
+    single-GPU launcher (main.py --gpu_ids N) moves the model to cuda:N without torch.cuda.set_device, so the
+    process default stays device 0: kernels, TMA descriptors, stream and SM-count lookups must all follow the
+    tensors, not the default."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kw):
+        dev = None
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                dev = a.device.index
+                break
+        if dev is None:
+            for a in kw.values():
+                if isinstance(a, torch.Tensor) and a.is_cuda:
+                    dev = a.device.index
+                    break
+        if dev is None or dev == torch.cuda.current_device():
+            return fn(self, *args, **kw)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kw)
+    return wrapper
+
+
+def _guard_all(cls):
+    for name, fn in list(vars(cls).items()):
+        if callable(fn) and not name.startswith("_") and name not in ("empty", "conv_geometry", "wgrad_workspace"):
+            setattr(cls, name, _device_guarded(fn))
+    return cls
 
 
 # launch counter: every successful C-ABI compute call == >=1 kernel launch of OUR kernels
@@ -151,6 +186,7 @@ def _req(t, dtype=torch.float32):
     return t
 
 
+@_guard_all
 class CudaBackend:
     """The one product backend: each method is one C-ABI entry point on torch's current stream.
     (tests/ substitute an oracle-backed emulation with the same method set to check the host
@@ -388,6 +424,11 @@ class CudaBackend:
                                        ptr(_req(indices, torch.int64)), stream()))
         LAUNCHES["n"] += 1
 
-    def check_fault(self):
+    def check_fault(self, device=None):
+        """Raise if a kernel on ``device`` (default: the current device) set the device fault word."""
         w = C.c_ulonglong(0)
+        if device is not None and torch.device(device).index not in (None, torch.cuda.current_device()):
+            with torch.cuda.device(device):
+                check(self.lib.bbdm_check_device_fault(stream(), C.byref(w)))
+            return
         check(self.lib.bbdm_check_device_fault(stream(), C.byref(w)))

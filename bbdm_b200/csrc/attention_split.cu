@@ -254,10 +254,10 @@ extern "C" int bbdm_attention_split(const void* qkv_hi, const void* qkv_lo, int 
 #define BBDM_AL(DD)                                                                                       \
   {                                                                                                       \
     const size_t smem = (size_t)2 * 4 * 64 * (DD + 8) * 2;                                                \
-    static bool cfgd = false;                                                                             \
-    if (!cfgd) {                                                                                          \
+    static DeviceOnce cfgd;                                                                                \
+    if (cfgd.need()) {                                                                                          \
       BBDM_CUDA_CHECK(cudaFuncSetAttribute(attention_split_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      cfgd = true;                                                                                        \
+      cfgd.mark();                                                                                         \
     }                                                                                                     \
     attention_split_kernel<DD><<<grid, 256, smem, s>>>(qh, ql, T, C, heads, order, scale_log2, out_f32, oh, ol); \
   }

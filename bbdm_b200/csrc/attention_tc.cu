@@ -376,10 +376,10 @@ extern "C" int bbdm_attention_tc(const void* qkv_hi, const void* qkv_lo, int B, 
   p.out_f32 = out_f32; p.out_hi = (__nv_bfloat16*)out_hi; p.out_lo = (__nv_bfloat16*)out_lo;
   p.fault = device_fault_ptr();
   BBDM_REQUIRE(p.fault != nullptr, "attention_tc: device fault word unavailable");
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     BBDM_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM));
-    configured = true;
+    configured.mark();
   }
   dim3 grid((T + AT_BQ - 1) / AT_BQ, B * heads);
   attention_tc_kernel<<<grid, 320, AT_SMEM, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], p);

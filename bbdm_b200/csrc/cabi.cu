@@ -21,9 +21,10 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 __device__ unsigned long long g_device_fault = 0ull;
 
 unsigned long long* device_fault_ptr() {
-  static unsigned long long* p = nullptr;
-  if (!p) cudaGetSymbolAddress((void**)&p, g_device_fault);
-  return p;
+  static unsigned long long* p[kMaxDevices] = {nullptr};   // the symbol has one instance per device
+  const int dev = current_device();
+  if (!p[dev]) cudaGetSymbolAddress((void**)&p[dev], g_device_fault);
+  return p[dev];
 }
 
 }  // namespace bbdm
@@ -55,7 +56,10 @@ int bbdm_check_device_fault(void* stream, unsigned long long* fault_word) {
   if (h) BBDM_CUDA_CHECK(cudaMemcpyAsync(p, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
   if (fault_word) *fault_word = h;
   if (h) {
-    bbdm::set_error("device fault word 0x%llx (kernel-side wait timeout)", h);
+    if ((h >> 28) == 0xBull)
+      bbdm::set_error("device fault word 0x%llx: timestep index out of range (the reference's gather raises IndexError)", h);
+    else
+      bbdm::set_error("device fault word 0x%llx (kernel-side wait timeout)", h);
     return BBDM_E_DEVICE;
   }
   return BBDM_OK;

@@ -31,16 +31,31 @@ unsigned long long* device_fault_ptr();
 
 #define BBDM_LAUNCH_CHECK() BBDM_CUDA_CHECK(cudaGetLastError())
 
-inline int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+// Everything cached on the host is cached PER DEVICE (the reference's single-GPU launcher puts the
+// model on cuda:N without cudaSetDevice-ing the process default; cabi.py guards the device per call).
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
+
+inline int num_sms() {
+  static int n[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (!n[dev]) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
+  }
+  return n[dev];
+}
+
+// one-time-per-device latch for cudaFuncSetAttribute (function attributes are per device)
+struct DeviceOnce {
+  bool done[kMaxDevices] = {false};
+  bool need() { return !done[current_device()]; }
+  void mark() { done[current_device()] = true; }
+};
 
 // ---- device helpers ----------------------------------------------------------------------
 __device__ __forceinline__ float silu_f(float x) {

@@ -436,10 +436,10 @@ static int launch_conv(const CUtensorMap* maps, const ConvParams& p, int grid, c
   constexpr int STAGES = PASSES == 3 ? Cfg::STAGES3 : Cfg::STAGES1;
   constexpr uint32_t STAGE_BYTES = PASSES == 3 ? Cfg::STAGE3 : Cfg::STAGE1;
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     BBDM_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<BN, PASSES, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configured.mark();
   }
   conv_umma_kernel<BN, PASSES, BK><<<grid, Cfg::THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5],
                                                               maps[6], maps[7], p);

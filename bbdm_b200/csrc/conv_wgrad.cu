@@ -346,10 +346,10 @@ static int launch_wgrad(const CUtensorMap* maps, const WgradParams& p, int grid,
   constexpr uint32_t STAGE_BYTES = 2 * (WG_BM * WG_BK * 2) + 2 * (BN / 64) * (WG_BK * 64 * 2);
   constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     BBDM_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    configured.mark();
   }
   conv_wgrad_kernel<BN><<<grid, WgCfg<BN>::THREADS, smem, s>>>(maps[0], maps[1], maps[2], maps[3], p);
   BBDM_LAUNCH_CHECK();

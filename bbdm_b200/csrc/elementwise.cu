@@ -14,10 +14,18 @@ __global__ void __launch_bounds__(256)
 q_sample_kernel(const float4* __restrict__ x0, const float4* __restrict__ y,
                 const float4* __restrict__ nz, const int64_t* __restrict__ t,
                 const float* __restrict__ m_tab, const float* __restrict__ v_tab,
-                float4* __restrict__ xt, float4* __restrict__ obj, int64_t n4_per_sample) {
+                float4* __restrict__ xt, float4* __restrict__ obj, int64_t n4_per_sample, int T,
+                unsigned long long* __restrict__ fault) {
   const int b = blockIdx.y;
-  const float m = m_tab[t[b]];
-  const float s = __fsqrt_rn(v_tab[t[b]]);
+  int64_t tb = t[b];
+  if (tb < 0 || tb >= T) {
+    // the reference's gather raises here (model/utils.py:6); kernels cannot raise: set the device fault word
+    // (bbdm_check_device_fault reports it) and read a valid row instead of out-of-bounds memory
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(fault, 0xB0000000ull | (unsigned)(tb & 0xFFFFFF));
+    tb = tb < 0 ? 0 : T - 1;
+  }
+  const float m = m_tab[tb];
+  const float s = __fsqrt_rn(v_tab[tb]);
   const float om = __fsub_rn(1.0f, m);
   const int64_t base = (int64_t)b * n4_per_sample;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4_per_sample;
@@ -109,10 +117,14 @@ nhwc_to_nchw_kernel(const float* __restrict__ src, int C, int64_t HW, float* __r
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ table, int rows, int width,
-                                   const int64_t* __restrict__ idx, float* __restrict__ out) {
+                                   const int64_t* __restrict__ idx, float* __restrict__ out,
+                                   unsigned long long* __restrict__ fault) {
   const int b = blockIdx.x;
   int64_t r = idx[b];
-  r = r < 0 ? 0 : (r >= rows ? rows - 1 : r);
+  if (r < 0 || r >= rows) {   // an index error in the reference; here: device fault word + a valid row
+    if (threadIdx.x == 0) atomicExch(fault, 0xB1000000ull | (unsigned)(r & 0xFFFFFF));
+    r = r < 0 ? 0 : rows - 1;
+  }
   for (int i = threadIdx.x; i < width; i += blockDim.x) out[(int64_t)b * width + i] = table[r * width + i];
 }
 
@@ -284,13 +296,15 @@ int bbdm_bridge_q_sample(const float* x0, const float* y, const float* noise, co
   BBDM_REQUIRE(x0 && y && noise && t && m_t && variance_t && x_t_out && objective_out, "q_sample: null pointer");
   BBDM_REQUIRE(B > 0 && B <= 65535 && n_per_sample > 0 && n_per_sample % 4 == 0,
                "q_sample: need 0 < B <= 65535 and n_per_sample %% 4 == 0 (got %d, %lld)", B, (long long)n_per_sample);
-  (void)num_timesteps;
+  BBDM_REQUIRE(num_timesteps > 0, "q_sample: num_timesteps must be > 0");
+  unsigned long long* fault = device_fault_ptr();
+  BBDM_REQUIRE(fault != nullptr, "q_sample: device fault word unavailable");
   const int64_t n4 = n_per_sample / 4;
   dim3 grid(grid_for(n4, 256, num_sms() * 8), B);
   cudaStream_t s = (cudaStream_t)stream;
 #define BBDM_QL(O)                                                                              \
   q_sample_kernel<O><<<grid, 256, 0, s>>>((const float4*)x0, (const float4*)y, (const float4*)noise, t, \
-                                          m_t, variance_t, (float4*)x_t_out, (float4*)objective_out, n4)
+                                          m_t, variance_t, (float4*)x_t_out, (float4*)objective_out, n4, num_timesteps, fault)
   if (objective == BBDM_OBJ_GRAD) BBDM_QL(BBDM_OBJ_GRAD);
   else if (objective == BBDM_OBJ_NOISE) BBDM_QL(BBDM_OBJ_NOISE);
   else if (objective == BBDM_OBJ_YSUBX) BBDM_QL(BBDM_OBJ_YSUBX);
@@ -363,7 +377,9 @@ int bbdm_nhwc_to_nchw(const float* src, int B, int H, int W, int C, float* out, 
 int bbdm_gather_rows(const float* table, int rows, int width, const int64_t* idx, int B, float* out,
                      void* stream) {
   BBDM_REQUIRE(table && idx && out && rows > 0 && width > 0 && B > 0, "gather_rows: bad args");
-  gather_rows_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(table, rows, width, idx, out);
+  unsigned long long* fault = device_fault_ptr();
+  BBDM_REQUIRE(fault != nullptr, "gather_rows: device fault word unavailable");
+  gather_rows_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(table, rows, width, idx, out, fault);
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
 }

@@ -263,10 +263,21 @@ class UNetEngine(KernelExecutor):
         w["film_n"] = off
         self._w = w
         self._wkey = key
-        if self._table is None or self._table.shape[0] < self.num_timesteps or self._table.device != dev:
-            # host-built with the reference's own expression (util.py:151-171): indexing is exact
-            tab = timestep_embedding(torch.arange(self.num_timesteps), u.model_channels)
+
+    def _embedding_table(self, dev):
+        """Rows 0..T-1 of the sinusoidal embedding (host-built with the reference's own expression,
+        util.py:151-171: indexing is exact).  T follows the owning bridge model (``unet.num_timesteps``, set by
+        BrownianBridgeModel.__init__) and is re-checked on every forward, outside the weight-key early return; an
+        index >= T sets the device fault word in bbdm_gather_rows (the reference computes the embedding for any
+        t, but its schedule gather raises for t >= T long before)."""
+        want = max(self.num_timesteps, int(getattr(self.unet, "num_timesteps", 0) or 0))
+        if self._table is None or self._table.shape[0] < want or self._table.device != dev:
+            self.num_timesteps = want
+            if self._table is not None:
+                self.generation += 1      # table address changes: captured graphs must be rebuilt
+            tab = timestep_embedding(torch.arange(want), self.unet.model_channels)
             self._table = tab.to(dev).contiguous()
+        return self._table
 
     # ------------------------------------------------------------------------------ blocks
     def _resblock(self, pool, name, m: ResBlock, src1, src2, film):
@@ -483,7 +494,7 @@ class UNetEngine(KernelExecutor):
         mc, ted = u.model_channels, u.model_channels * 4
         temb, e1, emb = pool.get((B, mc)), pool.get((B, ted)), pool.get((B, ted))
         film = pool.get((B, w["film_n"]))
-        be.gather_rows(self._table, t, temb)
+        be.gather_rows(self._embedding_table(dev), t, temb)
         l0, l2 = u.time_embed[0], u.time_embed[2]
         be.linear(temb, l0.weight.detach(), l0.bias.detach(), e1, act_out=True)
         be.linear(e1, l2.weight.detach(), l2.bias.detach(), emb)

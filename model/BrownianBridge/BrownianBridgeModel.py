@@ -51,6 +51,8 @@ class BrownianBridgeModel(nn.Module):
         self.channels = unet_params.in_channels
         self.condition_key = unet_params.condition_key
         self.denoise_fn = UNetModel(**vars(unet_params))
+        # plain attribute (not a parameter/buffer): sizes the engine's timestep-embedding table
+        self.denoise_fn.num_timesteps = int(self.num_timesteps)
         self._bridge = BridgeOps(self)
 
     def register_schedule(self):

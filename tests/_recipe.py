@@ -57,6 +57,13 @@ UNET_CONFIGS = {
                       attention_resolutions=(16, 8, 4), channel_mult=(1, 4, 8), conv_resample=True, dims=2,
                       num_heads=8, num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True,
                       use_spatial_transformer=False, context_dim=None, condition_key="nocond"),
+    # BASELINE configs[1]: the pixel template at UNet image_size 256 (T = 4096 attention in the middle block)
+    "cfg2": dict(image_size=256, in_channels=6, model_channels=128, out_channels=3,
+                 num_res_blocks=2, attention_resolutions=(32, 16, 8), channel_mult=(1, 4, 8),
+                 conv_resample=True, dims=2, num_heads=8, num_head_channels=64,
+                 use_scale_shift_norm=True, resblock_updown=True,
+                 use_spatial_transformer=False, context_dim=None,
+                 condition_key="SpatialRescaler"),
     "cfg1": dict(image_size=64, in_channels=6, model_channels=128, out_channels=3,
                  num_res_blocks=2, attention_resolutions=(32, 16, 8), channel_mult=(1, 4, 8),
                  conv_resample=True, dims=2, num_heads=8, num_head_channels=64,

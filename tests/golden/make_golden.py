@@ -125,11 +125,41 @@ def unet_and_psample(unet_name, B, tag, bb_kw=None, step_ids=(3, -1), with_loop=
           f"{os.path.getsize(path) / 1e3:.0f} kB")
 
 
+def cfg2_full_size(B=1):
+    """BASELINE configs[1] at FULL size (256x256 pixel BBDM, 200-step schedule): UNet forward, one mid-trajectory
+    and the final p_sample of the unmodified reference.  Inputs are regenerated by the tests from the same seeds
+    (synth_images / manual_seed), only the noise the reference drew and its outputs are stored (~5 MB)."""
+    net = build_ref("cfg2")
+    S, cx = 256, 3
+    x = synth_images((B, cx, S, S), seed=11)
+    y = synth_images((B, cx, S, S), seed=12)
+    t = torch.tensor([(517 + 311 * i) % 1000 for i in range(B)], dtype=torch.long)
+    data = {"t": t.numpy(), "unet_out": net.denoise_fn(x, timesteps=t, context=y).numpy()}
+    nsteps = len(net.steps)
+    ids = [100, nsteps - 1]
+    for i in ids:
+        xt = synth_images((B, cx, S, S), seed=100 + i)
+        torch.manual_seed(5000 + i)
+        out, x0r = net.p_sample(xt, y, y, i, clip_denoised=False)
+        torch.manual_seed(5000 + i)
+        nz = torch.randn_like(xt)
+        data[f"ps{i}_noise"] = nz.numpy()
+        data[f"ps{i}_out"], data[f"ps{i}_x0"] = out.numpy(), x0r.numpy()
+    data["ps_ids"] = np.array(ids)
+    path = os.path.join(HERE, "cfg2_b1.npz")
+    np.savez_compressed(path, **data)
+    print("cfg2_b1", f"{os.path.getsize(path) / 1e6:.1f} MB")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg1", action="store_true")
+    ap.add_argument("--cfg2-only", action="store_true", help="only the full-size 256x256 fixture (~2 min CPU)")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
+    if a.cfg2_only:
+        cfg2_full_size()
+        sys.exit(0)
     schedule_kats()
     unet_and_psample("tiny_pixel", 2, "tiny_pixel")
     unet_and_psample("tiny_latent", 3, "tiny_latent", bb_kw=dict(objective="noise", loss_type="l2"))

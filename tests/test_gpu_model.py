@@ -72,6 +72,29 @@ def test_unet_and_p_sample_match_reference_fixture(tag):
         assert d_loop < (2e-3 if kw.get("objective") == "noise" else 2e-4)
 
 
+def test_cfg2_full_size_matches_reference_fixture():
+    """BASELINE configs[1] -- the benchmarked configuration -- at FULL size (256x256 pixel BBDM, T = 4096 attention
+    inside the net, 256-wide tile geometry): UNet output, one mid-trajectory and the final p_sample against the
+    fixture the unmodified reference produced (tests/golden/make_golden.py --cfg2-only, B = 1).  B = 16 follows from
+    the bit-identical batch-independence property (test_full_resolution_batch_independence_and_determinism)."""
+    g = gold("cfg2_b1")
+    net = build("cfg2")
+    x = synth_images((1, 3, 256, 256), seed=11).cuda()
+    y = synth_images((1, 3, 256, 256), seed=12).cuda()
+    with torch.no_grad():
+        out = net.denoise_fn(x, timesteps=g["t"].cuda(), context=y)
+    d_unet = rel_dev(out, g["unet_out"])
+    devs = {}
+    for i in g["ps_ids"].tolist():
+        xt = synth_images((1, 3, 256, 256), seed=100 + i).cuda()
+        o, x0 = net.p_sample(xt, y, y, i, clip_denoised=False, noise=g[f"ps{i}_noise"].cuda())
+        devs[i] = (rel_dev(o, g[f"ps{i}_out"]), rel_dev(x0, g[f"ps{i}_x0"]))
+    net._bridge.backend().check_fault()
+    print(f"\n[cfg2 256x256] unet rel dev {d_unet:.3e}; p_sample (out, x0) rel dev {devs}")
+    assert d_unet < TOL_PSAMPLE
+    assert max(max(v) for v in devs.values()) < TOL_PSAMPLE
+
+
 def test_training_step_on_gpu():
     """forward -> loss -> backward on CUDA: fused q_sample kernel + autograd UNet graph."""
     g = gold("tiny_pixel")

@@ -122,6 +122,18 @@ def test_oracle_matches_full_size_fixture(tag):
     assert rel_dev(out, g["unet_out"]) < 2e-6
 
 
+def test_oracle_matches_cfg2_full_size_fixture():
+    """BASELINE configs[1] at full size (256x256, B = 1): the oracle's UNet forward against the fixture the
+    unmodified reference produced (one forward, ~20 s on 8 cores)."""
+    g = load("cfg2_b1")
+    cfg = O.unet_cfg(**UNET_CONFIGS["cfg2"])
+    sd = oracle_state("cfg2")
+    x = synth_images((1, 3, 256, 256), seed=11)
+    y = synth_images((1, 3, 256, 256), seed=12)
+    out = O.unet_forward(sd, cfg, x, g["t"], y)
+    assert rel_dev(out, g["unet_out"]) < 2e-6
+
+
 @pytest.mark.reference
 def test_oracle_matches_live_reference(ref_bbdm):
     """Fresh inputs (not in the fixtures) through the unmodified reference, live."""
