@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # BBDM_LIB selects another in-tree build of the same sources (A/B experiments, tools/); the product default is fixed
 LIB_PATH = os.environ.get("BBDM_LIB") or os.path.join(_HERE, "libbbdm_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OBJ = {"grad": 0, "noise": 1, "ysubx": 2}
 RESAMPLE_NONE, RESAMPLE_UP2, RESAMPLE_DOWN2 = 0, 1, 2
 RES_NONE, RES_SAME, RES_UP2, RES_DOWN2 = 0, 1, 2, 3
@@ -31,6 +31,7 @@ SYMBOLS = [
     "bbdm_attention", "bbdm_attention_split", "bbdm_attention_tc", "bbdm_conv_umma_geometry", "bbdm_gn_finalize_partials",
     "bbdm_split_grad", "bbdm_conv_wgrad_workspace", "bbdm_conv_wgrad", "bbdm_gn_bwd_reduce", "bbdm_gn_bwd_apply",
     "bbdm_conv_wgrad_direct", "bbdm_attention_bwd", "bbdm_conv_direct_pad", "bbdm_softmax_rows_split", "bbdm_vq_nearest", "bbdm_s2d_split", "bbdm_pack_weight_split_both",
+    "bbdm_wino_geometry", "bbdm_wino_input", "bbdm_wino_output", "bbdm_wino_pack_weight",
 ]
 
 
@@ -61,7 +62,22 @@ class ConvArgs(C.Structure):
                 ("residual", C.c_void_p), ("res_mode", C.c_int),
                 ("out", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
                 ("passes", C.c_int), ("out_nchw_channels", C.c_int), ("upsample2x", C.c_int),
-                ("stats_partial", C.c_void_p)]
+                ("stats_partial", C.c_void_p), ("weights_per_image", C.c_int), ("operand_f16", C.c_int)]
+
+
+class WinoInputArgs(C.Structure):
+    _fields_ = [("src1", C.c_void_p), ("c1", C.c_int), ("src2", C.c_void_p), ("c2", C.c_int),
+                ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("groups", C.c_int),
+                ("mean", C.c_void_p), ("rstd", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("film_scale", C.c_void_p), ("film_shift", C.c_void_p), ("film_stride", C.c_int64),
+                ("silu", C.c_int),
+                ("v_hi", C.c_void_p), ("v_lo", C.c_void_p), ("raw_hi", C.c_void_p), ("raw_lo", C.c_void_p)]
+
+
+class WinoOutputArgs(C.Structure):
+    _fields_ = [("m", C.c_void_p), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cout", C.c_int),
+                ("bias", C.c_void_p), ("residual", C.c_void_p), ("res_mode", C.c_int),
+                ("out", C.c_void_p), ("stats_partial", C.c_void_p)]
 
 
 class BbdmError(RuntimeError):
@@ -119,6 +135,10 @@ def load():
     lib.bbdm_vq_nearest.argtypes = [vp, vp, i64, i, i, vp, vp, vp]
     lib.bbdm_s2d_split.argtypes = [vp, i, i, i, i, vp, vp, vp]
     lib.bbdm_pack_weight_split_both.argtypes = [vp, i, i, i, vp, vp, vp, vp, vp]
+    lib.bbdm_wino_geometry.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i), C.POINTER(i64), C.POINTER(i)]
+    lib.bbdm_wino_input.argtypes = [C.POINTER(WinoInputArgs), vp]
+    lib.bbdm_wino_output.argtypes = [C.POINTER(WinoOutputArgs), vp]
+    lib.bbdm_wino_pack_weight.argtypes = [vp, i, i, vp, vp, vp]
     for s in SYMBOLS:
         fn = getattr(lib, s)
         if s not in ("bbdm_last_error",):
@@ -172,7 +192,7 @@ def _device_guarded(fn):
 
 def _guard_all(cls):
     for name, fn in list(vars(cls).items()):
-        if callable(fn) and not name.startswith("_") and name not in ("empty", "conv_geometry", "wgrad_workspace"):
+        if callable(fn) and not name.startswith("_") and name not in ("empty", "conv_geometry", "wgrad_workspace", "wino_geometry"):
             setattr(cls, name, _device_guarded(fn))
     return cls
 
@@ -309,11 +329,11 @@ class CudaBackend:
     def conv_umma(self, *, B, H, W, Cin, Cout, taps, a_hi, a_lo, w_hi, w_lo, bias=None, Cin2=0,
                   a2_hi=None, a2_lo=None, w2_hi=None, w2_lo=None, bias2=None, residual=None,
                   res_mode=RES_NONE, out=None, out_hi=None, out_lo=None, passes=3, out_nchw_channels=0,
-                  stats_partial=None, upsample2x=False):
+                  stats_partial=None, upsample2x=False, weights_per_image=False, operand_f16=False):
         a = ConvArgs(B, H, W, Cin, Cout, taps, ptr(a_hi), ptr(a_lo), ptr(w_hi), ptr(w_lo), ptr(bias),
                      Cin2, ptr(a2_hi), ptr(a2_lo), ptr(w2_hi), ptr(w2_lo), ptr(bias2),
                      ptr(residual), res_mode, ptr(out), ptr(out_hi), ptr(out_lo), passes, out_nchw_channels,
-                     int(upsample2x), ptr(stats_partial))
+                     int(upsample2x), ptr(stats_partial), int(weights_per_image), int(operand_f16))
         check(self.lib.bbdm_conv_umma(C.byref(a), stream()))
         LAUNCHES["n"] += 1
 
@@ -322,6 +342,36 @@ class CudaBackend:
         v = [C.c_int(0) for _ in range(4)]
         check(self.lib.bbdm_conv_umma_geometry(H, W, *[C.byref(z) for z in v]))
         return tuple(z.value for z in v)
+
+    # -- Winograd F(4x4,3x3) path ------------------------------------------------------------------
+    def wino_geometry(self, B, H, W):
+        """(tiles_h, tiles_w, tiles_total, eligible)."""
+        th, tw, el, tot = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int64(0)
+        check(self.lib.bbdm_wino_geometry(B, H, W, C.byref(th), C.byref(tw), C.byref(tot), C.byref(el)))
+        return th.value, tw.value, tot.value, bool(el.value)
+
+    def wino_input(self, src1, src2, *, groups, mean, rstd, gamma, beta, film_scale=None, film_shift=None,
+                   film_stride=0, silu=True, v_hi, v_lo, raw_hi=None, raw_lo=None):
+        B, H, W, c1 = src1.shape
+        a = WinoInputArgs(ptr(_req(src1)), c1, ptr(src2), 0 if src2 is None else src2.shape[3], B, H, W, groups,
+                          ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(film_scale), ptr(film_shift), film_stride,
+                          int(silu), ptr(_req(v_hi, torch.float16)), ptr(_req(v_lo, torch.float16)),
+                          ptr(raw_hi), ptr(raw_lo))
+        check(self.lib.bbdm_wino_input(C.byref(a), stream()))
+        LAUNCHES["n"] += 1
+
+    def wino_output(self, m, *, B, H, W, Cout, bias=None, residual=None, res_mode=RES_NONE, out, stats_partial=None):
+        a = WinoOutputArgs(ptr(_req(m)), B, H, W, Cout, ptr(bias), ptr(residual), res_mode, ptr(_req(out)),
+                           ptr(stats_partial))
+        check(self.lib.bbdm_wino_output(C.byref(a), stream()))
+        LAUNCHES["n"] += 1
+
+    def wino_pack_weight(self, w, u_hi, u_lo):
+        """w [Cout,Cin,3,3] fp32 -> u_hi/u_lo fp16 [36, Cout, Cin] (2^8 * G w G^T)."""
+        Cout, Cin = w.shape[0], w.shape[1]
+        check(self.lib.bbdm_wino_pack_weight(ptr(_req(w)), Cout, Cin, ptr(_req(u_hi, torch.float16)),
+                                             ptr(_req(u_lo, torch.float16)), stream()))
+        LAUNCHES["n"] += 1
 
     def gn_finalize_partials(self, part1, rows1, part2, rows2, B, hw, groups, eps, mean, rstd):
         c1 = part1.shape[1]

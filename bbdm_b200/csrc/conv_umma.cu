@@ -54,6 +54,8 @@ struct ConvParams {
   int taps;
   int up2;           // 1: fused nearest-2x upsample (4 output phases x 2x2 taps on the low-res input)
   int passes;
+  int w_per_image;   // 1: the weight "tap" index is the image index of the tile (36 Winograd position GEMMs in one launch)
+  int f16;           // 1: operand planes are fp16 (hi, lo) instead of bf16
   int kb_per_chunk;  // K blocks accumulated in TMEM before promotion to registers
   const float* bias; const float* bias2;
   const float* residual; int res_mode;
@@ -172,6 +174,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               wtap = phase * 4 + tap;
             } else if (p.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
             else if (p.taps == 4) { dy = tap >> 1; dx = tap & 1; }   // 2x2 window at (0..1, 0..1): zero pad bottom/right
+            else if (p.w_per_image) wtap = tb;                       // taps == 1: weights of transform position tb
             tma_load_4d(sbase, &map_a_hi, full, cb * BK, w0 + dx, h0 + dy, b0);
             if (PASSES == 3) tma_load_4d(sbase + OFF_ALO, &map_a_lo, full, cb * BK, w0 + dx, h0 + dy, b0);
             tma_load_3d(sbase + OFF_WHI, &map_w_hi, full, cb * BK, n0, wtap);
@@ -190,21 +193,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
     __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ============================================
-    // BBDM_UNIFORM_ISSUE (opt-in build flag, round-2 candidate, NOT yet validated on hardware for this kernel):
-    // the whole warp runs the loop in uniform control flow and only tcgen05.mma / commit sit under the elected
-    // lane's predicate, so ptxas keeps the descriptors in uniform registers.  The same change took the attention
-    // kernel from 5.8 to 4.0 ms; here it matters for the N = 64/128 tiles and the single-pass mode, where 12 (4)
-    // MMAs per K-block do not cover the ~250 issue-lane instructions spent on them (profiles/r01_ncu_attention_v6.md).
-#ifdef BBDM_UNIFORM_ISSUE
+    // Warp-uniform issue: the whole warp runs the loop in uniform control flow and only tcgen05.mma / commit sit
+    // under the elected lane's predicate, so ptxas keeps the descriptors in uniform registers (12 MMAs of a K-block:
+    // 30 straight-line instructions instead of 91 with an ELECT/BRA loop around each UTCHMMA).  Measured round 2
+    // (profiles/r02_uniform_issue_ab.md): cfg2 163.1 -> 160.2 ms, cfg1 4.64 -> 4.32 ms, cfg5 7.32 -> 7.14 ms.
     const bool leader = elect_one_sync();
     {
-#else
-    const bool leader = true;
-    if (lane == 0) {
-#endif
-      // instruction descriptor: D=f32, A=B=bf16, K-major both, N>>3 @17, M>>4 @24
-      constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                 ((uint32_t)(UM_BM >> 4) << 24);
+      // instruction descriptor: D=f32, A=B=bf16 (format 1) or fp16 (format 0), K-major both, N>>3 @17, M>>4 @24
+      const uint32_t IDESC = (1u << 4) | (p.f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(UM_BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -238,15 +235,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
               }
               tc_commit(bar_empty + 8 * stage);        // frees the smem slot when these MMAs retire
             }
-#ifdef BBDM_UNIFORM_ISSUE
             __syncwarp();
-#endif
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           if (leader) tc_commit(bar_tfull + 8 * acc);  // chunk complete -> promotion warps
-#ifdef BBDM_UNIFORM_ISSUE
           __syncwarp();
-#endif
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }
@@ -396,14 +389,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 
 // ------------------------------------------------------------------------------- host side
 // bf16 NHWC activation [B,H,W,C] -> 4-D map (C, W, H, B), box (64, TW, TH, TB), SWIZZLE_128B
-static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int TW, int TH, int TB, int BK) {
+static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int TW, int TH, int TB, int BK,
+                        bool f16 = false) {
   EncodeTiledFn enc = get_encode();
   BBDM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   BBDM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: %d (B=%d H=%d W=%d C=%d box=%dx%dx%d)",
@@ -412,14 +406,14 @@ static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, in
 }
 
 // bf16 weights [taps][Cout][Cin] -> 3-D map (Cin, Cout, taps), box (64, BN, 1)
-static int make_w_map(CUtensorMap* m, const void* ptr, int taps, int Cout, int Cin, int BN, int BK) {
+static int make_w_map(CUtensorMap* m, const void* ptr, int taps, int Cout, int Cin, int BN, int BK, bool f16 = false) {
   EncodeTiledFn enc = get_encode();
   BBDM_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
   cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
   cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
   cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+  CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   BBDM_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed: %d (taps=%d Cout=%d Cin=%d BN=%d)", (int)r,
@@ -493,6 +487,8 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   BBDM_REQUIRE(a->res_mode >= 0 && a->res_mode <= 3 && (a->res_mode == 0 || a->residual), "conv_umma: bad residual");
   if (a->res_mode == BBDM_RES_UP2 && !a->upsample2x) BBDM_REQUIRE(a->H % 2 == 0 && a->W % 2 == 0, "conv_umma: RES_UP2 needs even H, W");
   BBDM_REQUIRE(a->W >= 4, "conv_umma: W < 4 not supported (use conv_direct)");
+  const bool wpi = a->weights_per_image != 0, f16 = a->operand_f16 != 0;
+  if (wpi) BBDM_REQUIRE(a->taps == 1 && a->Cin2 == 0 && !a->upsample2x, "conv_umma: weights_per_image needs taps == 1 and no fused operand");
 
   ConvParams p;
   p.B = a->B; p.H = a->H; p.W = a->W; p.Cout = a->Cout;
@@ -519,7 +515,12 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   p.taps = a->taps;
   p.up2 = a->upsample2x ? 1 : 0;
   p.passes = a->passes;
-  p.kb_per_chunk = (a->passes == 3 ? 4 : 8) * (64 / BK);
+  p.w_per_image = wpi ? 1 : 0;
+  p.f16 = f16 ? 1 : 0;
+  // chunk length: 4 K-blocks (direct conv); 2 for the Winograd position GEMMs, whose output transform amplifies
+  // the truncation error of the TMEM accumulator (tools/studies/tmem_rz_accumulation.py)
+  p.kb_per_chunk = wpi ? 2 : (a->passes == 3 ? 4 : 8) * (64 / BK);
+  if (wpi) BBDM_REQUIRE(p.TB == 1, "conv_umma: weights_per_image needs 128-pixel tiles inside one image (H*W >= 128)");
   p.bias = a->bias; p.bias2 = a->Cin2 ? a->bias2 : nullptr;
   p.residual = a->residual; p.res_mode = a->res_mode;
   p.out = a->out; p.out_hi = (__nv_bfloat16*)a->out_hi; p.out_lo = (__nv_bfloat16*)a->out_lo;
@@ -534,16 +535,16 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
                "conv_umma: stats_partial needs a tile inside one image (H*W >= 128) and NHWC output");
   CUtensorMap maps[8];
   int rc;
-  if ((rc = make_act_map(&maps[0], a->a_hi, a->B, a->H, a->W, a->Cin, p.TW, p.TH, p.TB, BK))) return rc;
-  if ((rc = make_act_map(&maps[1], a->passes == 3 ? a->a_lo : a->a_hi, a->B, a->H, a->W, a->Cin, p.TW, p.TH, p.TB, BK))) return rc;
-  const int wtaps = a->upsample2x ? 16 : a->taps;
-  if ((rc = make_w_map(&maps[2], a->w_hi, wtaps, a->Cout, a->Cin, BN, BK))) return rc;
-  if ((rc = make_w_map(&maps[3], a->passes == 3 ? a->w_lo : a->w_hi, wtaps, a->Cout, a->Cin, BN, BK))) return rc;
+  if ((rc = make_act_map(&maps[0], a->a_hi, a->B, a->H, a->W, a->Cin, p.TW, p.TH, p.TB, BK, f16))) return rc;
+  if ((rc = make_act_map(&maps[1], a->passes == 3 ? a->a_lo : a->a_hi, a->B, a->H, a->W, a->Cin, p.TW, p.TH, p.TB, BK, f16))) return rc;
+  const int wtaps = a->upsample2x ? 16 : (wpi ? a->B : a->taps);
+  if ((rc = make_w_map(&maps[2], a->w_hi, wtaps, a->Cout, a->Cin, BN, BK, f16))) return rc;
+  if ((rc = make_w_map(&maps[3], a->passes == 3 ? a->w_lo : a->w_hi, wtaps, a->Cout, a->Cin, BN, BK, f16))) return rc;
   if (a->Cin2) {
-    if ((rc = make_act_map(&maps[4], a->a2_hi, a->B, a->H, a->W, a->Cin2, p.TW, p.TH, p.TB, BK))) return rc;
-    if ((rc = make_act_map(&maps[5], a->passes == 3 ? a->a2_lo : a->a2_hi, a->B, a->H, a->W, a->Cin2, p.TW, p.TH, p.TB, BK))) return rc;
-    if ((rc = make_w_map(&maps[6], a->w2_hi, 1, a->Cout, a->Cin2, BN, BK))) return rc;
-    if ((rc = make_w_map(&maps[7], a->passes == 3 ? a->w2_lo : a->w2_hi, 1, a->Cout, a->Cin2, BN, BK))) return rc;
+    if ((rc = make_act_map(&maps[4], a->a2_hi, a->B, a->H, a->W, a->Cin2, p.TW, p.TH, p.TB, BK, f16))) return rc;
+    if ((rc = make_act_map(&maps[5], a->passes == 3 ? a->a2_lo : a->a2_hi, a->B, a->H, a->W, a->Cin2, p.TW, p.TH, p.TB, BK, f16))) return rc;
+    if ((rc = make_w_map(&maps[6], a->w2_hi, 1, a->Cout, a->Cin2, BN, BK, f16))) return rc;
+    if ((rc = make_w_map(&maps[7], a->passes == 3 ? a->w2_lo : a->w2_hi, 1, a->Cout, a->Cin2, BN, BK, f16))) return rc;
   } else {
     maps[4] = maps[0]; maps[5] = maps[1]; maps[6] = maps[2]; maps[7] = maps[3];
   }

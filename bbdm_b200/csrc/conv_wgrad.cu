@@ -126,14 +126,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
-    // BBDM_UNIFORM_ISSUE: opt-in warp-uniform MMA issue (see conv_umma.cu); the default build is unchanged
-#ifdef BBDM_UNIFORM_ISSUE
+    // warp-uniform MMA issue (see conv_umma.cu)
     const bool leader = elect_one_sync();
     {
-#else
-    const bool leader = true;
-    if (lane == 0) {
-#endif
       // D=f32, A=B=bf16, A K-major, B MN-major (bit 16), N=BN, M=128
       constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
                                  ((uint32_t)(WG_BM >> 4) << 24);
@@ -166,15 +161,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g_hi, const __grid_con
               }
               tc_commit(bar_empty + 8 * stage);
             }
-#ifdef BBDM_UNIFORM_ISSUE
             __syncwarp();
-#endif
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           if (leader) tc_commit(bar_tfull + 8 * acc);
-#ifdef BBDM_UNIFORM_ISSUE
           __syncwarp();
-#endif
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
       }

@@ -1,0 +1,401 @@
+// Winograd F(4x4, 3x3) for the stride-1 3x3 convolutions of the ResBlocks (openaimodel.py:207,233):
+// 4x fewer tensor-core MACs than the direct implicit GEMM.
+//
+//   Y = A^T [ sum_ci (G g G^T) .* (B^T d B) ] A        per 4x4 output tile / 6x6 input tile
+//
+// Three kernels around the tcgen05 GEMM (bbdm_conv_umma, weights_per_image mode: 36 independent
+// [tiles x Cin] . [Cin x Cout] products, one per transform position):
+//   wino_input_kernel   x (fp32 NHWC, optionally a channel concat) -> GroupNorm affine (+FiLM) -> SiLU ->
+//                       V = B^T d B per 6x6 tile (zero padding applies to the ACTIVATED tensor) ->
+//                       split-fp16 planes V_hi, V_lo [36][tiles][C]; optionally also the split-bf16 planes of
+//                       the raw input (A operand of the ResBlock's 1x1 skip conv).  HBM-bound:
+//                       4 B read + 36/16 * 4 B written per input element.
+//   wino_weight_kernel  U = 2^8 * G g G^T (fp64 from the fp32 OIHW weight) -> split-fp16 [36][Cout][Cin].
+//   wino_output_kernel  M [36][tiles][Cout] fp32 -> Y = 2^-8 * A^T M A + bias (+ residual: same / nearest-up /
+//                       2x2-avg addressed) -> fp32 NHWC + fused GroupNorm partial sums of the result.
+//                       HBM-bound: 36/16 * 4 B read + 4 B written per output element.
+//
+// Numerics (tools/studies/split_formats_accuracy.py, tmem_rz_accumulation.py): split-FP16 operands carry 22
+// mantissa bits (bf16 pairs: 16), which pays for the F(4,3) transforms' error amplification: per-layer deviation
+// from the fp64 conv 3.0-3.6e-6 including the tensor core's truncating accumulator (chunks of 2 K-blocks), vs
+// 4.4e-6 for the direct split-bf16 kernel.  The weight planes are pre-scaled by 2^8 (exact) so that U_lo stays
+// a normal fp16 number; the output transform multiplies by 2^-8.
+#include "common.cuh"
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+namespace bbdm {
+
+constexpr float WINO_WSCALE = 256.0f;
+
+// ---- 1-D transforms (interpolation points 0, +-1, +-2; Lavin & Gray) -----------------------------
+// B^T (6x6) applied to d[0..5] with stride S in a register array
+template <int S>
+__device__ __forceinline__ void wino_bt6(float* d) {
+  const float d0 = d[0], d1 = d[S], d2 = d[2 * S], d3 = d[3 * S], d4 = d[4 * S], d5 = d[5 * S];
+  d[0] = fmaf(4.0f, d0, fmaf(-5.0f, d2, d4));
+  d[S] = fmaf(-4.0f, d1 + d2, d3 + d4);
+  d[2 * S] = fmaf(4.0f, d1 - d2, d4 - d3);
+  d[3 * S] = fmaf(2.0f, d3 - d1, d4 - d2);
+  d[4 * S] = fmaf(2.0f, d1 - d3, d4 - d2);
+  d[5 * S] = fmaf(4.0f, d1, fmaf(-5.0f, d3, d5));
+}
+// A^T (4x6) applied to m[0..5] (stride S) -> y[0..3] (stride T)
+template <int S, int T>
+__device__ __forceinline__ void wino_at6(const float* m, float* y) {
+  const float s12 = m[S] + m[2 * S], d12 = m[S] - m[2 * S];
+  const float s34 = m[3 * S] + m[4 * S], d34 = m[3 * S] - m[4 * S];
+  y[0] = (m[0] + s12) + s34;
+  y[T] = fmaf(2.0f, d34, d12);
+  y[2 * T] = fmaf(4.0f, s34, s12);
+  y[3 * T] = fmaf(8.0f, d34, d12) + m[5 * S];
+}
+
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// ------------------------------------------------------------------------------------------
+struct WinoInParams {
+  const float* src1; int c1;
+  const float* src2; int c2;
+  int B, H, W, C, groups, cpg, th, tw;
+  int64_t Mtot;
+  const float* mean; const float* rstd; const float* gamma; const float* beta;
+  const float* fscale; const float* fshift; int64_t fstride;
+  int silu;
+  __half* v_hi; __half* v_lo;
+  __nv_bfloat16* raw_hi; __nv_bfloat16* raw_lo;
+};
+
+// One CTA per (sample b, tile row ty, chunk of 256*VEC channels): every thread owns VEC channels and walks the tile
+// row left to right, keeping the two activated pixel columns it shares with the next tile in registers (24 instead of
+// 36 loads + activations per tile).  A warp reads 128*VEC contiguous bytes per pixel and writes 64*VEC contiguous
+// bytes per (position, tile) and plane.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+wino_input_kernel(const WinoInParams p) {
+  const int b = blockIdx.x / p.th, ty = blockIdx.x % p.th;
+  const int c = (blockIdx.y * 256 + threadIdx.x) * VEC;
+  if (c >= p.C) return;
+  // GroupNorm affine x FiLM of this sample for this thread's channels
+  float sc[VEC], sh[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const int g = (c + v) / p.cpg;
+    const float s0 = p.rstd[b * p.groups + g] * p.gamma[c + v];
+    const float h0 = p.beta[c + v] - p.mean[b * p.groups + g] * s0;
+    float f1 = 1.0f, f0 = 0.0f;
+    if (p.fscale) { f1 = 1.0f + p.fscale[(int64_t)b * p.fstride + c + v]; f0 = p.fshift[(int64_t)b * p.fstride + c + v]; }
+    sc[v] = s0 * f1;
+    sh[v] = fmaf(h0, f1, f0);
+  }
+  const float* base;
+  int cs, cc;
+  if (c < p.c1) { base = p.src1; cs = p.c1; cc = c; } else { base = p.src2; cs = p.c2; cc = c - p.c1; }
+  const int y0 = 4 * ty - 1;
+  float act[VEC][36];      // activated 6x6 tile, [row][col]
+  // load + activate columns [j0, 6) of the tile whose first input column is x0
+  auto fill = [&](int x0, int j0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int iy = y0 + i;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        if (j < j0) continue;
+        const int ix = x0 + j;
+        const bool in = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        float x[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) x[v] = 0.f;
+        if (in) {
+          const float* ptr = base + (((int64_t)b * p.H + iy) * p.W + ix) * cs + cc;
+          if (VEC == 2) { const float2 t = *reinterpret_cast<const float2*>(ptr); x[0] = t.x; x[VEC - 1] = t.y; }
+          else x[0] = *ptr;
+        }
+        if (p.raw_hi && i >= 1 && i <= 4 && j >= 2) {
+          // pixels this pass owns (tile interior rows; columns not seen by the previous tile): raw split-bf16 planes
+          // for the 1x1 skip conv.  Column j >= 2 of tile tx is input column 4*tx+1.. : every pixel exactly once,
+          // except input column 0 (j == 1 of tile 0), handled by j0 == 0 below.
+          const int64_t off = (((int64_t)b * p.H + iy) * p.W + ix) * p.C + c;
+          if (in) {
+            if (VEC == 2) {
+              uint32_t h, l;
+              split2x(x[0], x[VEC - 1], h, l);
+              *reinterpret_cast<uint32_t*>(p.raw_hi + off) = h;
+              *reinterpret_cast<uint32_t*>(p.raw_lo + off) = l;
+            } else {
+              split_bf16(x[0], p.raw_hi[off], p.raw_lo[off]);
+            }
+          }
+        } else if (p.raw_hi && i >= 1 && i <= 4 && j == 1 && j0 == 0 && in) {
+          const int64_t off = (((int64_t)b * p.H + iy) * p.W + ix) * p.C + c;
+          if (VEC == 2) {
+            uint32_t h, l;
+            split2x(x[0], x[VEC - 1], h, l);
+            *reinterpret_cast<uint32_t*>(p.raw_hi + off) = h;
+            *reinterpret_cast<uint32_t*>(p.raw_lo + off) = l;
+          } else {
+            split_bf16(x[0], p.raw_hi[off], p.raw_lo[off]);
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          float a = fmaf(x[v], sc[v], sh[v]);
+          if (p.silu) a = __fdividef(a, 1.0f + __expf(-a));
+          act[v][i * 6 + j] = in ? a : 0.f;       // the conv zero-pads the ACTIVATED tensor
+        }
+      }
+    }
+  };
+  for (int tx = 0; tx < p.tw; ++tx) {
+    if (tx == 0) fill(-1, 0);
+    else {
+      // columns 4, 5 of the previous tile are columns 0, 1 of this one
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { act[v][i * 6] = act[v][i * 6 + 4]; act[v][i * 6 + 1] = act[v][i * 6 + 5]; }
+      fill(4 * tx - 1, 2);
+    }
+    // V = B^T d B: columns, then rows (on a copy: `act` carries over to the next tile)
+    float t[VEC][36];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+      for (int q = 0; q < 36; ++q) t[v][q] = act[v][q];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) wino_bt6<6>(t[v] + j);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) wino_bt6<1>(t[v] + 6 * i);
+    }
+    const int64_t m = ((int64_t)b * p.th + ty) * p.tw + tx;
+#pragma unroll
+    for (int q = 0; q < 36; ++q) {
+      const int64_t off = ((int64_t)q * p.Mtot + m) * p.C + c;
+      if (VEC == 2) {
+        uint32_t h, l;
+        split2_f16(t[0][q], t[VEC - 1][q], h, l);
+        *reinterpret_cast<uint32_t*>(p.v_hi + off) = h;
+        *reinterpret_cast<uint32_t*>(p.v_lo + off) = l;
+      } else {
+        const __half h = __float2half_rn(t[0][q]);
+        p.v_hi[off] = h;
+        p.v_lo[off] = __float2half_rn(t[0][q] - __half2float(h));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+struct WinoOutParams {
+  const float* m; int64_t Mtot;
+  int B, H, W, Cout, th, tw;
+  const float* bias;
+  const float* residual; int res_mode;
+  float* out;
+  float* stats;      // [B*th][Cout][2] or nullptr
+};
+
+// One CTA per (64-channel group, tile row ty, sample b): 32 channel pairs x 8 tile-column lanes.
+__global__ void __launch_bounds__(256)
+wino_output_kernel(const WinoOutParams p) {
+  __shared__ float red[8][64][2];
+  const int cg = blockIdx.x, ty = blockIdx.y, b = blockIdx.z;
+  const int lane = threadIdx.x & 31, tl = threadIdx.x >> 5;
+  const int c = cg * 64 + lane * 2;
+  float2 bv = make_float2(0.f, 0.f);
+  if (p.bias) bv = *reinterpret_cast<const float2*>(p.bias + c);
+  float sum0 = 0.f, sum1 = 0.f, sq0 = 0.f, sq1 = 0.f;
+  const float inv = 1.0f / WINO_WSCALE;
+  for (int tx = tl; tx < p.tw; tx += 8) {
+    const int64_t m = ((int64_t)b * p.th + ty) * p.tw + tx;
+    float mx[36], my[36];
+#pragma unroll
+    for (int q = 0; q < 36; ++q) {
+      const float2 v = *reinterpret_cast<const float2*>(p.m + ((int64_t)q * p.Mtot + m) * p.Cout + c);
+      mx[q] = v.x; my[q] = v.y;
+    }
+    // Y = A^T M A: columns (6 -> 4 rows), then rows (6 -> 4 columns)
+    float tx4[24], ty4[24], yx[16], yy[16];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { wino_at6<6, 6>(mx + j, tx4 + j); wino_at6<6, 6>(my + j, ty4 + j); }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { wino_at6<1, 1>(tx4 + 6 * i, yx + 4 * i); wino_at6<1, 1>(ty4 + 6 * i, yy + 4 * i); }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int hh = 4 * ty + i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ww = 4 * tx + j;
+        float r0 = fmaf(yx[i * 4 + j], inv, bv.x), r1 = fmaf(yy[i * 4 + j], inv, bv.y);
+        if (p.res_mode == BBDM_RES_SAME) {
+          const float2 t = *reinterpret_cast<const float2*>(p.residual + (((int64_t)b * p.H + hh) * p.W + ww) * p.Cout + c);
+          r0 += t.x; r1 += t.y;
+        } else if (p.res_mode == BBDM_RES_UP2) {
+          const float2 t = *reinterpret_cast<const float2*>(
+              p.residual + (((int64_t)b * (p.H >> 1) + (hh >> 1)) * (p.W >> 1) + (ww >> 1)) * p.Cout + c);
+          r0 += t.x; r1 += t.y;
+        } else if (p.res_mode == BBDM_RES_DOWN2) {
+          const int64_t W2 = (int64_t)p.W * 2;
+          const float* rp = p.residual + (((int64_t)b * p.H * 2 + hh * 2) * W2 + ww * 2) * p.Cout + c;
+          const float2 t0 = *reinterpret_cast<const float2*>(rp), t1 = *reinterpret_cast<const float2*>(rp + p.Cout);
+          const float2 t2 = *reinterpret_cast<const float2*>(rp + W2 * p.Cout);
+          const float2 t3 = *reinterpret_cast<const float2*>(rp + (W2 + 1) * p.Cout);
+          r0 += 0.25f * (((t0.x + t1.x) + t2.x) + t3.x);
+          r1 += 0.25f * (((t0.y + t1.y) + t2.y) + t3.y);
+        }
+        *reinterpret_cast<float2*>(p.out + (((int64_t)b * p.H + hh) * p.W + ww) * p.Cout + c) = make_float2(r0, r1);
+        sum0 += r0; sum1 += r1;
+        sq0 = fmaf(r0, r0, sq0); sq1 = fmaf(r1, r1, sq1);
+      }
+    }
+  }
+  if (p.stats) {
+    // fixed-order combine of the 8 tile-column lanes => deterministic partial sums
+    red[tl][lane * 2][0] = sum0; red[tl][lane * 2][1] = sq0;
+    red[tl][lane * 2 + 1][0] = sum1; red[tl][lane * 2 + 1][1] = sq1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float a = 0.f, q = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a += red[k][threadIdx.x][0]; q += red[k][threadIdx.x][1]; }
+      const int64_t prow = (int64_t)b * p.th + ty;
+      *reinterpret_cast<float2*>(p.stats + (prow * p.Cout + cg * 64 + threadIdx.x) * 2) = make_float2(a, q);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// U[q][co][ci] = 2^8 * (G g G^T)[q] in fp64, split into fp16 planes.  One thread per (co, ci).
+__global__ void __launch_bounds__(256)
+wino_weight_kernel(const float* __restrict__ w, int Cout, int Cin, __half* __restrict__ u_hi, __half* __restrict__ u_lo) {
+  const int64_t n = (int64_t)Cout * Cin;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    double g[3][3], t[6][3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) g[i / 3][i % 3] = (double)w[idx * 9 + i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double g0 = g[0][j], g1 = g[1][j], g2 = g[2][j];
+      t[0][j] = g0 / 4.0;
+      t[1][j] = -(g0 + g1 + g2) / 6.0;
+      t[2][j] = -(g0 - g1 + g2) / 6.0;
+      t[3][j] = g0 / 24.0 + g1 / 12.0 + g2 / 6.0;
+      t[4][j] = g0 / 24.0 - g1 / 12.0 + g2 / 6.0;
+      t[5][j] = g2;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const double g0 = t[i][0], g1 = t[i][1], g2 = t[i][2];
+      double u[6];
+      u[0] = g0 / 4.0;
+      u[1] = -(g0 + g1 + g2) / 6.0;
+      u[2] = -(g0 - g1 + g2) / 6.0;
+      u[3] = g0 / 24.0 + g1 / 12.0 + g2 / 6.0;
+      u[4] = g0 / 24.0 - g1 / 12.0 + g2 / 6.0;
+      u[5] = g2;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const float v = (float)(u[j] * (double)WINO_WSCALE);
+        const __half h = __float2half_rn(v);
+        const __half l = __float2half_rn(v - __half2float(h));
+        const int64_t off = (int64_t)(i * 6 + j) * n + idx;
+        u_hi[off] = h;
+        u_lo[off] = l;
+      }
+    }
+  }
+}
+
+}  // namespace bbdm
+
+using namespace bbdm;
+
+extern "C" {
+
+int bbdm_wino_geometry(int B, int H, int W, int* tiles_h, int* tiles_w, int64_t* tiles_total, int* eligible) {
+  BBDM_REQUIRE(B > 0 && H > 0 && W > 0, "wino_geometry: bad shape");
+  const int th = H / 4, tw = W / 4;
+  const int64_t mtot = (int64_t)B * th * tw;
+  if (tiles_h) *tiles_h = th;
+  if (tiles_w) *tiles_w = tw;
+  if (tiles_total) *tiles_total = mtot;
+  // the GEMM views the tile axis as rows of 16 with 128-tile M blocks inside one transform position
+  if (eligible) *eligible = (H % 4 == 0 && W % 4 == 0 && mtot % 16 == 0 && mtot >= 128) ? 1 : 0;
+  return BBDM_OK;
+}
+
+int bbdm_wino_input(const BbdmWinoInputArgs* a, void* stream) {
+  BBDM_REQUIRE(a && a->src1 && a->v_hi && a->v_lo, "wino_input: null args");
+  WinoInParams p;
+  p.src1 = a->src1; p.c1 = a->c1;
+  p.src2 = a->src2; p.c2 = a->src2 ? a->c2 : 0;
+  p.B = a->B; p.H = a->H; p.W = a->W;
+  p.C = p.c1 + p.c2;
+  p.groups = a->groups;
+  BBDM_REQUIRE(p.B > 0 && p.H > 0 && p.W > 0 && p.H % 4 == 0 && p.W % 4 == 0, "wino_input: H, W must be multiples of 4");
+  BBDM_REQUIRE(p.c1 % 2 == 0 && p.c2 % 2 == 0 && p.C > 0, "wino_input: channel counts must be even");
+  BBDM_REQUIRE(a->mean && a->rstd && a->gamma && a->beta && p.groups > 0 && p.C % p.groups == 0,
+               "wino_input: incomplete GroupNorm args");
+  BBDM_REQUIRE((a->film_scale == nullptr) == (a->film_shift == nullptr), "wino_input: film scale/shift mismatch");
+  BBDM_REQUIRE((a->raw_hi == nullptr) == (a->raw_lo == nullptr), "wino_input: raw hi/lo must come in pairs");
+  p.cpg = p.C / p.groups;
+  p.th = p.H / 4; p.tw = p.W / 4;
+  p.Mtot = (int64_t)p.B * p.th * p.tw;
+  p.mean = a->mean; p.rstd = a->rstd; p.gamma = a->gamma; p.beta = a->beta;
+  p.fscale = a->film_scale; p.fshift = a->film_shift; p.fstride = a->film_stride;
+  p.silu = a->silu;
+  p.v_hi = (__half*)a->v_hi; p.v_lo = (__half*)a->v_lo;
+  p.raw_hi = (__nv_bfloat16*)a->raw_hi; p.raw_lo = (__nv_bfloat16*)a->raw_lo;
+  const int64_t ctas = (int64_t)p.B * p.th;
+  BBDM_REQUIRE(ctas < (1ll << 31), "wino_input: too many tile rows");
+  static int vec = 0;       // BBDM_WINO_IN_VEC=1|2: channels per thread (A/B switch; default 1)
+  if (!vec) { const char* e = getenv("BBDM_WINO_IN_VEC"); vec = (e && atoi(e) == 2) ? 2 : 1; }
+  if (vec == 2) {
+    dim3 grid((unsigned)ctas, (p.C / 2 + 255) / 256);
+    wino_input_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  } else {
+    dim3 grid((unsigned)ctas, (p.C + 255) / 256);
+    wino_input_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  }
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
+int bbdm_wino_output(const BbdmWinoOutputArgs* a, void* stream) {
+  BBDM_REQUIRE(a && a->m && a->out, "wino_output: null args");
+  WinoOutParams p;
+  p.m = a->m;
+  p.B = a->B; p.H = a->H; p.W = a->W; p.Cout = a->Cout;
+  BBDM_REQUIRE(p.B > 0 && p.B <= 65535 && p.H > 0 && p.W > 0 && p.H % 4 == 0 && p.W % 4 == 0,
+               "wino_output: H, W must be multiples of 4 (B <= 65535)");
+  BBDM_REQUIRE(p.Cout > 0 && p.Cout % 64 == 0, "wino_output: Cout %% 64 != 0");
+  BBDM_REQUIRE(a->res_mode >= 0 && a->res_mode <= 3 && (a->res_mode == 0 || a->residual), "wino_output: bad residual");
+  if (a->res_mode == BBDM_RES_UP2) BBDM_REQUIRE(p.H % 2 == 0 && p.W % 2 == 0, "wino_output: RES_UP2 needs even H, W");
+  p.th = p.H / 4; p.tw = p.W / 4;
+  BBDM_REQUIRE(p.th <= 65535, "wino_output: too many tile rows");
+  p.Mtot = (int64_t)p.B * p.th * p.tw;
+  p.bias = a->bias; p.residual = a->residual; p.res_mode = a->res_mode;
+  p.out = a->out; p.stats = a->stats_partial;
+  dim3 grid(p.Cout / 64, p.th, p.B);
+  wino_output_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
+int bbdm_wino_pack_weight(const float* w, int Cout, int Cin, void* u_hi, void* u_lo, void* stream) {
+  BBDM_REQUIRE(w && u_hi && u_lo && Cout > 0 && Cin > 0, "wino_pack_weight: bad args");
+  const int64_t n = (int64_t)Cout * Cin;
+  int64_t g = (n + 255) / 256;
+  if (g > (int64_t)num_sms() * 16) g = (int64_t)num_sms() * 16;
+  wino_weight_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, (__half*)u_hi, (__half*)u_lo);
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
+}  // extern "C"

@@ -12,6 +12,8 @@ logic (block wiring, concat order, FiLM offsets, skip modes) on CPU; the product
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -74,6 +76,11 @@ class KernelExecutor:
         self._pools = {}
         self._gn_ws = None
         self._geom_cache = {}
+        # Winograd F(4x4,3x3) for the stride-1 3x3 convs with at least this many input and output channels
+        # (parity mode only; below that the transform traffic outweighs the 4x MAC saving).  BBDM_WINOGRAD=0 disables.
+        self.wino = precision == "split3" and os.environ.get("BBDM_WINOGRAD", "1") != "0"
+        self.wino_min_c = int(os.environ.get("BBDM_WINO_MIN_C", "256"))
+        self._wino_geom = {}
 
     def _umma_ok(self, cin, cout, w):
         return cin % 64 == 0 and cout % 64 == 0 and w >= 4
@@ -155,6 +162,45 @@ class KernelExecutor:
         if r is None:
             r = self._geom_cache[key] = self.be.conv_geometry(H, W)[3]
         return r
+
+
+    # ---- Winograd F(4x4,3x3) path (csrc/winograd.cu) ----------------------------------------------------------
+    def _wino_geometry(self, B, H, W):
+        key = (B, H, W)
+        g = self._wino_geom.get(key)
+        if g is None:
+            g = self._wino_geom[key] = self.be.wino_geometry(B, H, W)
+        return g
+
+    def _wino_ok(self, ent, B, H, W):
+        return bool(self.wino and "u_hi" in ent and self._wino_geometry(B, H, W)[3])
+
+    def _wino_conv(self, pool, ent, src1, src2, *, mean, rstd, gamma, beta, film=None, silu=True, raw=None,
+                   residual=None, res_mode=cabi.RES_NONE, stats=True):
+        """GroupNorm-affine(+FiLM)+SiLU -> 3x3 conv (+bias, +residual) of cat(src1, src2) on the Winograd path:
+        input transform -> 36 position GEMMs in one tcgen05 launch -> output transform (+ GN partial sums).
+        raw = (r_hi, r_lo): also emit the raw input's split-bf16 planes (operand of a 1x1 skip conv)."""
+        be = self.be
+        B, H, W, _ = src1.shape
+        cin, cout = ent["cin"], ent["cout"]
+        th, tw, mtot, _ = self._wino_geometry(B, H, W)
+        v_hi, v_lo = pool.get((36, mtot, cin), torch.float16), pool.get((36, mtot, cin), torch.float16)
+        fkw = {} if film is None else dict(film_scale=film[0], film_shift=film[1], film_stride=film[2])
+        rkw = {} if raw is None else dict(raw_hi=raw[0], raw_lo=raw[1])
+        be.wino_input(src1, src2, groups=GN_GROUPS, mean=mean, rstd=rstd, gamma=gamma, beta=beta, silu=silu,
+                      v_hi=v_hi, v_lo=v_lo, **fkw, **rkw)
+        mbuf = pool.get((36, mtot, cout))
+        be.conv_umma(B=36, H=mtot // 16, W=16, Cin=cin, Cout=cout, taps=1, a_hi=v_hi, a_lo=v_lo, w_hi=ent["u_hi"],
+                     w_lo=ent["u_lo"], out=mbuf, passes=3, weights_per_image=True, operand_f16=True)
+        pool.put(v_hi, v_lo)
+        out = pool.get((B, H, W, cout))
+        part = pool.get((B * th, cout, 2)) if stats else None
+        be.wino_output(mbuf, B=B, H=H, W=W, Cout=cout, bias=ent["bias"], residual=residual, res_mode=res_mode,
+                       out=out, stats_partial=part)
+        pool.put(mbuf)
+        if part is not None:
+            out._gn = (part, th)
+        return out
 
 
 class UNetEngine(KernelExecutor):
@@ -244,6 +290,20 @@ class UNetEngine(KernelExecutor):
                 film_b.append(b)
                 w[name + "#film"] = (off, n)
                 off += n
+        if self.wino:
+            # stride-1 3x3 ResBlock convs: Winograd-domain weight planes U = 2^8 G g G^T, fp16 hi/lo [36][Cout][Cin]
+            for name, m in u.named_modules():
+                if not isinstance(m, ResBlock) or not m.use_scale_shift_norm:
+                    continue
+                for cname, conv, skip in ((name + ".in_layers.2", m.in_layers[2], m.up or m.down),
+                                          (name + ".out_layers.3", m.out_layers[3], False)):
+                    ent = w[cname]
+                    if skip or "hi" not in ent or ent["k"] != 3 or min(ent["cin"], ent["cout"]) < self.wino_min_c:
+                        continue
+                    uh = buf(cname, "u_hi", (36, ent["cout"], ent["cin"]), torch.float16)
+                    ul = buf(cname, "u_lo", (36, ent["cout"], ent["cin"]), torch.float16)
+                    be.wino_pack_weight(conv.weight.detach().contiguous(), uh, ul)
+                    ent["u_hi"], ent["u_lo"] = uh, ul
         for name, m in u.named_modules():
             if isinstance(m, ResBlock) and m.up and m.channels % 64 == 0 and m.out_channels % 64 == 0:
                 # up-ResBlock in_layers conv: 16 phase taps of the fused nearest-2x + 3x3 conv
@@ -323,6 +383,17 @@ class UNetEngine(KernelExecutor):
                                        None, cabi.RES_UP2, None, None, None)
         shp = (B, H, W, cin)
         a_f32 = a_hi = a_lo = r_f32 = r_hi = r_lo = None
+        if umma1 and resample == cabi.RESAMPLE_NONE and not need_raw_f32 and m.use_scale_shift_norm \
+                and self._wino_ok(e1, B, H, W):
+            # Winograd conv1; the raw split planes for a fused 1x1 skip come out of the same input pass
+            if fuse_skip:
+                r_hi, r_lo = pool.get(shp, torch.bfloat16), pool.get(shp, torch.bfloat16)
+            h1 = self._wino_conv(pool, e1, src1, src2, mean=mean, rstd=rstd, gamma=gn.weight.detach(),
+                                 beta=gn.bias.detach(), raw=(r_hi, r_lo) if fuse_skip else None)
+            pool.put(mean, rstd)
+            return self._resblock_tail(pool, name, m, src1, h1, film, foff, cout, (B, H, W), e2, es, umma2,
+                                       (es, r_hi, r_lo) if fuse_skip else None, resample_to_res(resample),
+                                       None, r_hi, r_lo, skip_conv=skip_conv, need_raw_f32=False)
         if umma1:
             a_hi, a_lo = pool.get(shp, torch.bfloat16), pool.get(shp, torch.bfloat16)
         else:
@@ -364,6 +435,25 @@ class UNetEngine(KernelExecutor):
         gn2 = m.out_layers[0]
         shp2 = (B, H, W, cout)
         b_f32 = b_hi = b_lo = None
+        if umma2 and m.use_scale_shift_norm and self._wino_ok(e2, B, H, W):
+            # Winograd conv2: the 1x1 skip (if any) runs as its own tensor-core GEMM and enters as the residual
+            residual, res_mode, skip_out = None, cabi.RES_NONE, None
+            if second is not None:
+                skip_out, _, _ = self._conv(pool, second[0], a_hi=second[1], a_lo=second[2], shape=(B, H, W))
+                residual, res_mode = skip_out, cabi.RES_SAME
+            elif skip_conv:
+                skip_out, _, _ = self._conv(pool, es, a_f32=r_f32, shape=(B, H, W))
+                residual, res_mode = skip_out, cabi.RES_SAME
+            elif need_raw_f32:
+                residual, res_mode = r_f32, cabi.RES_SAME
+            else:
+                residual, res_mode = src1, id_res_mode
+            out = self._wino_conv(pool, e2, h1, None, mean=mean, rstd=rstd, gamma=gn2.weight.detach(),
+                                  beta=gn2.bias.detach(),
+                                  film=(film[:, foff:foff + cout], film[:, foff + cout:foff + 2 * cout], film.shape[1]),
+                                  residual=residual, res_mode=res_mode)
+            pool.put(mean, rstd, h1, r_f32, r_hi, r_lo, skip_out)
+            return out
         if umma2:
             b_hi, b_lo = pool.get(shp2, torch.bfloat16), pool.get(shp2, torch.bfloat16)
         else:

@@ -12,9 +12,11 @@ Execution:
   * no-grad CUDA calls (sampling, validation) go to :class:`bbdm_b200.engine.UNetEngine`,
     i.e. the hand-written sm_100a kernels behind the C ABI.  There is no CPU path: a CPU
     tensor raises.
-  * calls that need autograd (training) run ``_forward_autograd`` -- a plain PyTorch graph over
-    the same parameters (library kernels).  Native backward kernels are the next row of
-    SURVEY section 8 (DESIGN.md "Scope").
+  * calls that need autograd (training) run ``_forward_autograd``: an autograd graph over the same
+    parameters whose nodes are the native kernels too (``bbdm_b200/train.py``: tcgen05 conv
+    forward / data gradient / weight gradient, fused GroupNorm+FiLM+SiLU backward, flash-style
+    attention backward); skip concats, residual adds, the time-embedding MLP and the loss stay
+    stock tensor ops.  ``NATIVE_TRAIN_CONV = False`` runs the whole graph on library kernels.
 """
 from __future__ import annotations
 

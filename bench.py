@@ -262,13 +262,34 @@ def main():
             e0.record()
             super().conv_umma(**kw)
             e1.record()
-            if kw.get("upsample2x"):
+            if kw.get("weights_per_image"):
+                # Winograd F(4x4,3x3) position GEMMs (B = 36 positions, H*W = tiles): the reference algorithm is the
+                # 3x3 conv over 16 pixels per tile (the kernel does 4x fewer MACs); the two transform kernels are
+                # timed into the same family below (wino_input / wino_output)
+                flops = 2.0 * kw["H"] * kw["W"] * 16 * kw["Cout"] * 9 * kw["Cin"]
+            elif kw.get("upsample2x"):
                 # reference algorithm: 3x3 conv on the 2x-upsampled tensor (the kernel does 2.25x fewer MACs)
                 flops = 2.0 * kw["B"] * 4 * kw["H"] * kw["W"] * kw["Cout"] * 9 * kw["Cin"]
             else:
                 flops = 2.0 * kw["B"] * kw["H"] * kw["W"] * kw["Cout"] * (kw["taps"] * kw["Cin"] + kw.get("Cin2", 0))
             ProfilingBackend.events.append((e0, e1, flops, {k: kw[k] for k in ("B", "H", "W", "Cin", "Cout", "taps")} |
-                                            {"Cin2": kw.get("Cin2", 0), "up2": bool(kw.get("upsample2x")), "res": kw.get("res_mode", 0)}))
+                                            {"Cin2": kw.get("Cin2", 0), "up2": bool(kw.get("upsample2x")), "res": kw.get("res_mode", 0),
+                                             "wino": bool(kw.get("weights_per_image"))}))
+
+        def _timed_transform(self, name, fn, *a, **kw):
+            if not ProfilingBackend.record:
+                return fn(*a, **kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(*a, **kw)
+            e1.record()
+            ProfilingBackend.events.append((e0, e1, 0.0, {"transform": name}))     # time counts, no extra FLOPs
+
+        def wino_input(self, *a, **kw):
+            return self._timed_transform("wino_input", super().wino_input, *a, **kw)
+
+        def wino_output(self, *a, **kw):
+            return self._timed_transform("wino_output", super().wino_output, *a, **kw)
 
     BridgeOps.backend_factory = staticmethod(lambda: ProfilingBackend())
     net = BrownianBridgeModel(namespace(cfg["unet"], cfg["sample_step"])).eval()
@@ -334,6 +355,7 @@ def main():
         yd = y_host.to(dev, non_blocking=True)
         o, _ = net.p_sample(xd, yd, ctx_of(yd), (10 + i) % (n_sched - 1))   # the public API call of the loop body
         out_host.copy_(o, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                        # the D2H must have landed before the host reads it
         x_host.copy_(out_host)                                           # next step's host-side input
     e3.record()
     barrier()
@@ -373,7 +395,9 @@ def main():
             for e0_, e1_, fl, shp in ProfilingBackend.events:
                 ms_ = e0_.elapsed_time(e1_)
                 f.write(json.dumps({**shp, "ms": ms_, "algo_tflops": fl / ms_ / 1e9}) + "\n")
-    n_conv = len(ProfilingBackend.events)
+    n_conv = sum(1 for e in ProfilingBackend.events if "transform" not in e[3])
+    n_wino = sum(1 for e in ProfilingBackend.events if e[3].get("wino"))
+    wino_tf_ms = sum(e[0].elapsed_time(e[1]) for e in ProfilingBackend.events if "transform" in e[3])
     peaks, peak_src = load_peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     achieved_tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
@@ -383,12 +407,15 @@ def main():
         traffic = json.load(open(tp)).get("dram_bytes_per_launch_mean")
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": traffic,
-                "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM conv, %d launches/step)" % n_conv,
+                "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM conv, %d launches/step, %d of them Winograd F(4x4,3x3) "
+                          "position GEMMs whose input/output transform kernels -- %.2f ms/step -- are included in kernel_ms)"
+                          % (n_conv, n_wino, wino_tf_ms),
                 "algorithmic_flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms,
                 "share_of_step": conv_ms / ms_dev if ms_dev else None,
                 "peak_source": peak_src + ", bf16 sustained",
-                "note": ("algorithmic FLOPs (2*M*N*K of the reference conv); precision mode '%s' issues %dx that on the "
-                         "tensor pipe" % (args.precision, 3 if args.precision == "split3" else 1))}
+                "note": ("algorithmic FLOPs (2*M*N*K of the reference conv); precision mode '%s' issues %dx the executed "
+                         "MACs on the tensor pipe; Winograd layers execute 1/4, fused-upsample layers 1/2.25 of the "
+                         "reference MACs" % (args.precision, 3 if args.precision == "split3" else 1))}
 
     if rank == 0:
         cpu = None

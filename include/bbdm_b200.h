@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BBDM_ABI_VERSION 1
+#define BBDM_ABI_VERSION 2
 
 enum {
   BBDM_OK = 0,
@@ -222,6 +222,11 @@ typedef struct {
                                  (128-pixel tile, 32-row warp slice); rows_per_image from
                                  bbdm_conv_umma_geometry.  Ignored (must be NULL) when a tile spans
                                  several images (tiles_per_image == 0).                         */
+  int weights_per_image;      /* 1 (taps must be 1): w_hi/w_lo hold one [Cout][Cin] matrix PER IMAGE, [B][Cout][Cin],
+                                 and image b is multiplied by matrix b -- B independent GEMMs in one launch (the 36
+                                 transform positions of the Winograd path, bbdm_wino_*).  Needs H*W >= 128.  */
+  int operand_f16;            /* 1: every operand plane is IEEE fp16 (hi = fp16(x), lo = fp16(x - hi)) instead of
+                                 bf16 -- 22 instead of 16 mantissa bits, values must stay below 65504        */
 } BbdmConvArgs;
 int bbdm_conv_umma(const BbdmConvArgs* a, void* stream);
 
@@ -235,6 +240,50 @@ int bbdm_conv_umma_geometry(int H, int W, int* TW, int* TH, int* TB, int* rows_p
 int bbdm_gn_finalize_partials(const float* part1, int c1, int rows1, const float* part2, int c2,
                               int rows2, int B, int hw, int groups, float eps, float* mean,
                               float* rstd, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Winograd F(4x4, 3x3) path for the stride-1 3x3 ResBlock convolutions (openaimodel.py:207,233): 4x fewer
+ * tensor-core MACs.  conv = wino_input -> bbdm_conv_umma(weights_per_image, operand_f16; B = 36 positions,
+ * H = tiles/16, W = 16, taps = 1, out = M) -> wino_output.  Split-FP16 operands keep the deviation from the
+ * fp32 reference below the direct split-bf16 kernel's.
+ * ------------------------------------------------------------------------------------------ */
+
+/* tiles_h = H/4, tiles_w = W/4, tiles_total = B*tiles_h*tiles_w; eligible = 1 iff H, W are multiples of 4 and
+ * tiles_total is a multiple of 16 and >= 128 (the GEMM's M blocking). */
+int bbdm_wino_geometry(int B, int H, int W, int* tiles_h, int* tiles_w, int64_t* tiles_total, int* eligible);
+
+/* cat(src1, src2) [B,H,W,C] fp32 -> act = silu?(GN_affine(x) * (1+film_scale) + film_shift) (as bbdm_prep_operand)
+ * -> V = B^T act B for every 6x6 tile (stride 4, origin (-1,-1), zero padding of the ACTIVATED tensor) ->
+ * split-fp16 planes v_hi, v_lo [36][tiles_total][C].  raw_hi/raw_lo (optional): split-bf16 NHWC planes of the
+ * raw input (A operand of the ResBlock's 1x1 skip convolution, openaimodel.py:244). */
+typedef struct {
+  const float* src1; int c1;
+  const float* src2; int c2;
+  int B, H, W;
+  int groups;
+  const float* mean; const float* rstd; const float* gamma; const float* beta;
+  const float* film_scale; const float* film_shift; int64_t film_stride;
+  int silu;
+  void* v_hi; void* v_lo;
+  void* raw_hi; void* raw_lo;
+} BbdmWinoInputArgs;
+int bbdm_wino_input(const BbdmWinoInputArgs* a, void* stream);
+
+/* m [36][tiles_total][Cout] fp32 (the position GEMMs' output) -> out [B,H,W,Cout] = 2^-8 * A^T m A + bias
+ * (+ residual, addressed as in BbdmConvArgs.res_mode), and optionally the GroupNorm partial sums of the result:
+ * stats_partial [B * tiles_h][Cout][2] (rows_per_image = tiles_h for bbdm_gn_finalize_partials). */
+typedef struct {
+  const float* m;
+  int B, H, W, Cout;
+  const float* bias;
+  const float* residual; int res_mode;
+  float* out;
+  float* stats_partial;
+} BbdmWinoOutputArgs;
+int bbdm_wino_output(const BbdmWinoOutputArgs* a, void* stream);
+
+/* w [Cout,Cin,3,3] fp32 -> U = 2^8 * G w G^T (fp64 arithmetic), split-fp16 planes u_hi, u_lo [36][Cout][Cin]. */
+int bbdm_wino_pack_weight(const float* w, int Cout, int Cin, void* u_hi, void* u_lo, void* stream);
 
 /* General fp32 direct convolution on CUDA cores (any Cin/Cout, k in {1,3}, stride 1 or 2,
  * pad k/2): stem (openaimodel.py:524), head (:690), conv-mode Downsample/Upsample (:109,150)

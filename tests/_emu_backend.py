@@ -126,8 +126,16 @@ class EmuBackend:
     def conv_umma(self, *, B, H, W, Cin, Cout, taps, a_hi, a_lo, w_hi, w_lo, bias=None, Cin2=0,
                   a2_hi=None, a2_lo=None, w2_hi=None, w2_lo=None, bias2=None, residual=None,
                   res_mode=0, out=None, out_hi=None, out_lo=None, passes=3, out_nchw_channels=0,
-                  stats_partial=None, upsample2x=False):
+                  stats_partial=None, upsample2x=False, weights_per_image=False, operand_f16=False):
         self.calls.append("conv_umma")
+        if weights_per_image:
+            # B independent GEMMs: image b [H*W, Cin] x matrix b [Cout, Cin]^T
+            assert taps == 1 and Cin2 == 0 and H * W >= 128 and operand_f16 == (a_hi.dtype == torch.float16)
+            a = self._planes(a_hi, a_lo).reshape(B, H * W, Cin)
+            w = self._planes(w_hi, w_lo).reshape(B, Cout, Cin)
+            assert not torch.isnan(a).any() and not torch.isnan(w).any()
+            out.copy_(torch.bmm(a, w.transpose(1, 2)).reshape(out.shape))
+            return
         if upsample2x:
             return self._conv_up2(B, H, W, Cin, Cout, a_hi, a_lo, w_hi, w_lo, bias, residual, res_mode, out,
                                   stats_partial)
@@ -190,6 +198,65 @@ class EmuBackend:
             rows = stats_partial.shape[0] // B
             assert rows == 4 * self.conv_geometry(H, W)[3] and rows > 0
             sp = stats_partial.view(B, rows, Cout, 2)
+            sp.zero_()
+            sp[:, 0, :, 0] = o.reshape(B, -1, Cout).sum(1)
+            sp[:, 0, :, 1] = (o.reshape(B, -1, Cout) ** 2).sum(1)
+        out.copy_(o)
+
+    # -- Winograd F(4x4,3x3): the kernels' transform formulation, literally ---------------------------------
+    _BT = torch.tensor([[4, 0, -5, 0, 1, 0], [0, -4, -4, 1, 1, 0], [0, 4, -4, -1, 1, 0],
+                        [0, -2, -1, 2, 1, 0], [0, 2, -1, -2, 1, 0], [0, 4, 0, -5, 0, 1]], dtype=torch.float64)
+    _G = torch.tensor([[1 / 4, 0, 0], [-1 / 6, -1 / 6, -1 / 6], [-1 / 6, 1 / 6, -1 / 6],
+                       [1 / 24, 1 / 12, 1 / 6], [1 / 24, -1 / 12, 1 / 6], [0, 0, 1]], dtype=torch.float64)
+    _AT = torch.tensor([[1, 1, 1, 1, 1, 0], [0, 1, -1, 2, -2, 0], [0, 1, 1, 4, 4, 0], [0, 1, -1, 8, -8, 1]],
+                       dtype=torch.float64)
+
+    def wino_geometry(self, B, H, W):
+        th, tw = H // 4, W // 4
+        tot = B * th * tw
+        return th, tw, tot, (H % 4 == 0 and W % 4 == 0 and tot % 16 == 0 and tot >= 128)
+
+    def _write_split_f16(self, x, hi, lo):
+        h = x.float().to(torch.float16)
+        hi.copy_(h)
+        lo.copy_((x.float() - h.float()).to(torch.float16))
+
+    def wino_input(self, src1, src2, *, groups, mean, rstd, gamma, beta, film_scale=None, film_shift=None,
+                   film_stride=0, silu=True, v_hi, v_lo, raw_hi=None, raw_lo=None):
+        self.calls.append("wino_input")
+        x = src1 if src2 is None else torch.cat([src1, src2], dim=3)
+        assert not torch.isnan(x).any()
+        B, H, W, C = x.shape
+        a = O.op_gn_act(x, mean, rstd, gamma, beta, film_scale, film_shift, silu, 0)        # [B,H,W,C]
+        t = F.pad(a.permute(0, 3, 1, 2).double(), (1, 1, 1, 1)).unfold(2, 6, 4).unfold(3, 6, 4)   # [B,C,th,tw,6,6]
+        V = torch.einsum("ij,bcxyjk,lk->ilbxyc", self._BT, t, self._BT)                      # [6,6,B,th,tw,C]
+        self._write_split_f16(V.reshape(v_hi.shape), v_hi, v_lo)
+        if raw_hi is not None:
+            self._write_split(x, raw_hi, raw_lo)
+
+    def wino_pack_weight(self, w, u_hi, u_lo):
+        self.calls.append("wino_pack_weight")
+        U = torch.einsum("ij,kcjl,ml->imkc", self._G, w.double(), self._G) * 256.0           # [6,6,Cout,Cin]
+        self._write_split_f16(U.reshape(u_hi.shape), u_hi, u_lo)
+
+    def wino_output(self, m, *, B, H, W, Cout, bias=None, residual=None, res_mode=0, out, stats_partial=None):
+        self.calls.append("wino_output")
+        assert not torch.isnan(m).any()
+        th, tw = H // 4, W // 4
+        M = m.double().reshape(6, 6, B, th, tw, Cout)
+        Y = torch.einsum("ij,jlbxyc,ml->bxiymc", self._AT, M, self._AT) / 256.0             # [B,th,4,tw,4,Cout]
+        o = Y.reshape(B, H, W, Cout).float()
+        if bias is not None:
+            o = o + bias
+        if res_mode == 1:
+            o = o + residual.reshape(B, H, W, Cout)
+        elif res_mode == 2:
+            o = o + O.op_resample(residual.reshape(B, H // 2, W // 2, Cout), 1)
+        elif res_mode == 3:
+            o = o + O.op_resample(residual.reshape(B, H * 2, W * 2, Cout), 2)
+        if stats_partial is not None:
+            assert stats_partial.shape[0] == B * th
+            sp = stats_partial.view(B, th, Cout, 2)
             sp.zero_()
             sp[:, 0, :, 0] = o.reshape(B, -1, Cout).sum(1)
             sp[:, 0, :, 1] = (o.reshape(B, -1, Cout) ** 2).sum(1)

@@ -55,6 +55,8 @@ def test_struct_layouts_match_header_field_order():
     assert fields("BbdmPSampleCoef") == [f[0] for f in cabi.PSampleCoef._fields_]
     assert fields("BbdmPrepArgs") == [f[0] for f in cabi.PrepArgs._fields_]
     assert fields("BbdmConvArgs") == [f[0] for f in cabi.ConvArgs._fields_]
+    assert fields("BbdmWinoInputArgs") == [f[0] for f in cabi.WinoInputArgs._fields_]
+    assert fields("BbdmWinoOutputArgs") == [f[0] for f in cabi.WinoOutputArgs._fields_]
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

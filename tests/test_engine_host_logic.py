@@ -46,6 +46,25 @@ def test_engine_wiring_matches_reference_fixture(tag, tol, expect_umma):
     assert torch.equal(out, out2)
 
 
+def test_winograd_path_wiring_matches_reference_fixture():
+    """The Winograd F(4x4,3x3) route of the ResBlock convs (input transform -> 36 position GEMMs -> output transform,
+    1x1 skip as a separate GEMM entering as the residual, GN partial sums from the output transform), forced on for
+    the 64-channel 32x32 level of mid_pixel (B*8*8 = 128 tiles) through the emulation backend."""
+    g = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLD, "mid_pixel.npz")).items() if v.ndim}
+    net = build("mid_pixel")
+    be = EmuBackend()
+    eng = UNetEngine(net, backend=be)
+    assert eng.wino
+    eng.wino_min_c = 64
+    out = eng.forward(g["x"], g["t"], g["y"])
+    assert be.calls.count("wino_input") >= 4 and be.calls.count("wino_input") == be.calls.count("wino_output")
+    assert not torch.isnan(out).any()
+    assert rel_dev(out, g["unet_out"]) < 6e-5
+    eng2 = UNetEngine(net, backend=EmuBackend())
+    eng2.wino = False
+    assert rel_dev(out, eng2.forward(g["x"], g["t"], g["y"])) < 8e-5     # both are within 6e-5 of the reference
+
+
 def test_weight_cache_refresh_on_param_change():
     net = build("tiny_latent")
     be = EmuBackend()
