@@ -32,6 +32,7 @@ SYMBOLS = [
     "bbdm_split_grad", "bbdm_conv_wgrad_workspace", "bbdm_conv_wgrad", "bbdm_gn_bwd_reduce", "bbdm_gn_bwd_apply",
     "bbdm_conv_wgrad_direct", "bbdm_attention_bwd", "bbdm_conv_direct_pad", "bbdm_softmax_rows_split", "bbdm_vq_nearest", "bbdm_s2d_split", "bbdm_pack_weight_split_both",
     "bbdm_wino_geometry", "bbdm_wino_input", "bbdm_wino_output", "bbdm_wino_pack_weight",
+    "bbdm_optim_chunk_elems", "bbdm_adam_multi", "bbdm_ema_multi", "bbdm_denorm_to_uint8",
 ]
 
 
@@ -139,6 +140,10 @@ def load():
     lib.bbdm_wino_input.argtypes = [C.POINTER(WinoInputArgs), vp]
     lib.bbdm_wino_output.argtypes = [C.POINTER(WinoOutputArgs), vp]
     lib.bbdm_wino_pack_weight.argtypes = [vp, i, i, vp, vp, vp]
+    lib.bbdm_denorm_to_uint8.argtypes = [vp, i, i, i, i, i, vp, vp]
+    lib.bbdm_optim_chunk_elems.argtypes = []
+    lib.bbdm_adam_multi.argtypes = [vp, vp, vp, vp, vp, vp, i, vp, vp, f, f, f, f, f, i64, vp, C.c_double, vp]
+    lib.bbdm_ema_multi.argtypes = [vp, vp, vp, vp, vp, i, vp, C.c_double, i, vp]
     for s in SYMBOLS:
         fn = getattr(lib, s)
         if s not in ("bbdm_last_error",):
@@ -192,7 +197,7 @@ def _device_guarded(fn):
 
 def _guard_all(cls):
     for name, fn in list(vars(cls).items()):
-        if callable(fn) and not name.startswith("_") and name not in ("empty", "conv_geometry", "wgrad_workspace", "wino_geometry"):
+        if callable(fn) and not name.startswith("_") and name not in ("empty", "conv_geometry", "wgrad_workspace", "wino_geometry", "optim_chunk_elems"):
             setattr(cls, name, _device_guarded(fn))
     return cls
 
@@ -371,6 +376,32 @@ class CudaBackend:
         Cout, Cin = w.shape[0], w.shape[1]
         check(self.lib.bbdm_wino_pack_weight(ptr(_req(w)), Cout, Cin, ptr(_req(u_hi, torch.float16)),
                                              ptr(_req(u_lo, torch.float16)), stream()))
+        LAUNCHES["n"] += 1
+
+    # -- sample_to_eval output path ------------------------------------------------------------------------
+    def denorm_to_uint8(self, images, to_normal, out):
+        B, Cc, H, W = images.shape
+        check(self.lib.bbdm_denorm_to_uint8(ptr(_req(images)), B, Cc, H, W, int(to_normal), ptr(_req(out, torch.uint8)),
+                                            stream()))
+        LAUNCHES["n"] += 1
+
+    # -- multi-tensor optimizer / EMA -----------------------------------------------------------------------
+    def optim_chunk_elems(self):
+        return int(self.lib.bbdm_optim_chunk_elems())
+
+    def adam_multi(self, tab, exp_avg, exp_avg_sq, *, lr, beta1, beta2, eps, weight_decay, step, ema_shadow=None,
+                   ema_decay=0.0):
+        """tab: bbdm_b200.optim.TensorTable (device pointer / size / chunk arrays of the parameter list)."""
+        check(self.lib.bbdm_adam_multi(ptr(tab.params), ptr(tab.grads), ptr(tab.numel), ptr(tab.offsets),
+                                       ptr(tab.chunk_tensor), ptr(tab.chunk_index), tab.n_chunks, ptr(_req(exp_avg)),
+                                       ptr(_req(exp_avg_sq)), lr, beta1, beta2, eps, weight_decay, int(step),
+                                       ptr(ema_shadow), float(ema_decay), stream()))
+        LAUNCHES["n"] += 1
+
+    def ema_multi(self, tab, shadow, decay, with_decay=True):
+        check(self.lib.bbdm_ema_multi(ptr(tab.params), ptr(tab.numel), ptr(tab.offsets), ptr(tab.chunk_tensor),
+                                      ptr(tab.chunk_index), tab.n_chunks, ptr(_req(shadow)), float(decay), int(with_decay),
+                                      stream()))
         LAUNCHES["n"] += 1
 
     def gn_finalize_partials(self, part1, rows1, part2, rows2, B, hw, groups, eps, mean, rstd):

@@ -519,7 +519,7 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   p.f16 = f16 ? 1 : 0;
   // chunk length: 4 K-blocks (direct conv); 2 for the Winograd position GEMMs, whose output transform amplifies
   // the truncation error of the TMEM accumulator (tools/studies/tmem_rz_accumulation.py)
-  p.kb_per_chunk = wpi ? 2 : (a->passes == 3 ? 4 : 8) * (64 / BK);
+  p.kb_per_chunk = (wpi ? 2 : (a->passes == 3 ? 4 : 8)) * (64 / BK);
   if (wpi) BBDM_REQUIRE(p.TB == 1, "conv_umma: weights_per_image needs 128-pixel tiles inside one image (H*W >= 128)");
   p.bias = a->bias; p.bias2 = a->Cin2 ? a->bias2 : nullptr;
   p.residual = a->residual; p.res_mode = a->res_mode;

@@ -283,6 +283,27 @@ static inline int grid_for(int64_t n, int block, int max_blocks) {
   return (int)g;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Output path of sample_to_eval (runners/utils.py:67-74): NCHW fp32 in [-1,1] (or [0,1]) -> NHWC uint8, the
+// reference's op order with one fp32 rounding per torch op, truncating cast (torch .to(uint8)) => byte-exact.
+//   x = clamp(x*0.5 + 0.5, 0, 1)   (to_normal)      y = clamp(x*255 + 0.5, 0, 255)      u8 = (uint8) y
+// One thread per pixel: coalesced reads per channel plane, C contiguous bytes written per pixel.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+denorm_to_uint8_kernel(const float* __restrict__ x, int C, int64_t HW, int to_normal, uint8_t* __restrict__ out) {
+  const int b = blockIdx.y;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
+    uint8_t* o = out + ((int64_t)b * HW + p) * C;
+    for (int c = 0; c < C; ++c) {
+      float v = x[((int64_t)b * C + c) * HW + p];
+      if (to_normal) v = fminf(fmaxf(__fadd_rn(__fmul_rn(v, 0.5f), 0.5f), 0.0f), 1.0f);
+      v = fminf(fmaxf(__fadd_rn(__fmul_rn(v, 255.0f), 0.5f), 0.0f), 255.0f);
+      o[c] = (uint8_t)v;          // truncation toward zero, like tensor.to(torch.uint8)
+    }
+  }
+}
+
 }  // namespace bbdm
 
 using namespace bbdm;
@@ -451,6 +472,16 @@ int bbdm_pack_weight_f32(const float* w, int Cout, int Cin, int k, float* out, v
   BBDM_REQUIRE(w && out && Cout > 0 && Cin > 0 && (k == 1 || k == 3), "pack_weight_f32: bad args");
   const int64_t n = (int64_t)k * k * Cout * Cin;
   pack_weight_f32_kernel<<<grid_for(n, 256, num_sms() * 8), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, k * k, out);
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
+/* images [B,C,H,W] fp32 -> uint8 [B,H,W,C] (the PNG byte layout PIL takes). */
+int bbdm_denorm_to_uint8(const float* images, int B, int C, int H, int W, int to_normal, uint8_t* out, void* stream) {
+  BBDM_REQUIRE(images && out && B > 0 && B <= 65535 && C > 0 && H > 0 && W > 0, "denorm_to_uint8: bad args");
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid(grid_for(HW, 256, num_sms() * 8), B);
+  denorm_to_uint8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(images, C, HW, to_normal, out);
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
 }

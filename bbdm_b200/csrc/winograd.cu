@@ -192,6 +192,139 @@ wino_input_kernel(const WinoInParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Shared-memory staged input transform (the default): one CTA per (sample b, tile row ty, 64-channel chunk) walks the
+// tile row in segments of 8 tiles.  Per segment: (1) cp.async stages the 6 x 34 pixel x 64 channel input patch
+// (double buffered: the next segment's loads fly while this one is transformed -- the register variant above is
+// bound by exposed load latency, ncu: 65 % long-scoreboard stalls, 29 % issue utilisation); (2) every pixel is
+// activated ONCE in place (GroupNorm affine x FiLM, SiLU; out-of-image pixels become exact zeros = the conv padding
+// of the activated tensor); (3) thread (tile, channel pair) reads its 6x6 tile with conflict-free 8-byte LDS,
+// transforms, splits to fp16 hi/lo and stores (128 contiguous bytes per warp, position and plane).
+constexpr int WI_CC = 64;                 // channels per CTA
+constexpr int WI_TX = 8;                  // tiles per segment
+constexpr int WI_COLS = 4 * WI_TX + 2;    // patch columns
+constexpr int WI_PATCH = 6 * WI_COLS * WI_CC;          // floats per buffer
+constexpr size_t WI_SMEM = 2 * (size_t)WI_PATCH * sizeof(float);
+
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2)
+wino_input_smem_kernel(const WinoInParams p) {
+  extern __shared__ __align__(16) float patch[];          // [2][6][WI_COLS][WI_CC]
+  const int b = blockIdx.x / p.th, ty = blockIdx.x % p.th;
+  const int cbase = blockIdx.y * WI_CC;                    // first channel of this CTA (in the concatenation)
+  const float* base;
+  int cs, cc0;
+  if (cbase < p.c1) { base = p.src1; cs = p.c1; cc0 = cbase; } else { base = p.src2; cs = p.c2; cc0 = cbase - p.c1; }
+  const int y0 = 4 * ty - 1;
+  const int tid = threadIdx.x;
+  const int ch4 = tid & 15;                                // this thread's 4-channel group in phases 1/2
+  const int pix0 = tid >> 4;                               // first patch pixel of this thread (stride 16 pixels)
+  constexpr int NPIX = 6 * WI_COLS;                        // 204 pixels per patch
+
+  // GroupNorm affine x FiLM for the 4 channels this thread activates
+  float sc[4], sh[4];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const int c = cbase + ch4 * 4 + v;
+    const int g = c / p.cpg;
+    const float s0 = p.rstd[b * p.groups + g] * p.gamma[c];
+    const float h0 = p.beta[c] - p.mean[b * p.groups + g] * s0;
+    float f1 = 1.0f, f0 = 0.0f;
+    if (p.fscale) { f1 = 1.0f + p.fscale[(int64_t)b * p.fstride + c]; f0 = p.fshift[(int64_t)b * p.fstride + c]; }
+    sc[v] = s0 * f1;
+    sh[v] = fmaf(h0, f1, f0);
+  }
+  const int nseg = (p.tw + WI_TX - 1) / WI_TX;
+  const uint32_t patch_s = (uint32_t)__cvta_generic_to_shared(patch);
+
+  auto stage = [&](int seg, int buf) {
+    const int x0 = 4 * WI_TX * seg - 1;
+    for (int px = pix0; px < NPIX; px += 16) {
+      const int i = px / WI_COLS, j = px - i * WI_COLS;
+      const int iy = y0 + i, ix = x0 + j;
+      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+        cp_async16(patch_s + (uint32_t)(((buf * NPIX + px) * WI_CC + ch4 * 4) * 4),
+                   base + (((int64_t)b * p.H + iy) * p.W + ix) * cs + cc0 + ch4 * 4);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  stage(0, 0);
+  for (int seg = 0; seg < nseg; ++seg) {
+    const int buf = seg & 1;
+    if (seg + 1 < nseg) {
+      stage(seg + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    float* pb = patch + buf * WI_PATCH;
+    const int x0 = 4 * WI_TX * seg - 1;
+    // ---- phase 2: activate every staged pixel once, in place ------------------------------------------------
+    for (int px = pix0; px < NPIX; px += 16) {
+      const int i = px / WI_COLS, j = px - i * WI_COLS;
+      const int iy = y0 + i, ix = x0 + j;
+      float4* q = reinterpret_cast<float4*>(pb + px * WI_CC + ch4 * 4);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+        const float4 x = *q;
+        if (p.raw_hi && i >= 1 && i <= 4 && j >= 1 && j <= 4 * WI_TX) {
+          // pixels this segment owns: raw split-bf16 planes for the 1x1 skip conv
+          uint2 h, l;
+          split4(x, h, l);
+          const int64_t off = (((int64_t)b * p.H + iy) * p.W + ix) * p.C + cbase + ch4 * 4;
+          *reinterpret_cast<uint2*>(p.raw_hi + off) = h;
+          *reinterpret_cast<uint2*>(p.raw_lo + off) = l;
+        }
+        a.x = fmaf(x.x, sc[0], sh[0]); a.y = fmaf(x.y, sc[1], sh[1]);
+        a.z = fmaf(x.z, sc[2], sh[2]); a.w = fmaf(x.w, sc[3], sh[3]);
+        if (p.silu) {
+          a.x = __fdividef(a.x, 1.0f + __expf(-a.x)); a.y = __fdividef(a.y, 1.0f + __expf(-a.y));
+          a.z = __fdividef(a.z, 1.0f + __expf(-a.z)); a.w = __fdividef(a.w, 1.0f + __expf(-a.w));
+        }
+      }
+      *q = a;                                              // out of the image: exact zero (padding of the activation)
+    }
+    __syncthreads();
+    // ---- phase 3: one (tile, channel pair) per thread -------------------------------------------------------
+    const int txl = tid >> 5, c0 = (tid & 31) * 2;
+    const int tx = WI_TX * seg + txl;
+    if (tx < p.tw) {
+      float t0[36], t1[36];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const float2 v = *reinterpret_cast<const float2*>(pb + ((i * WI_COLS + 4 * txl + j) * WI_CC + c0));
+          t0[i * 6 + j] = v.x;
+          t1[i * 6 + j] = v.y;
+        }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) { wino_bt6<6>(t0 + j); wino_bt6<6>(t1 + j); }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { wino_bt6<1>(t0 + 6 * i); wino_bt6<1>(t1 + 6 * i); }
+      const int64_t m = ((int64_t)b * p.th + ty) * p.tw + tx;
+      const int64_t plane = p.Mtot * p.C;
+      __half* ph = p.v_hi + m * p.C + cbase + c0;
+      __half* pl = p.v_lo + m * p.C + cbase + c0;
+#pragma unroll
+      for (int q = 0; q < 36; ++q) {
+        uint32_t h, l;
+        split2_f16(t0[q], t1[q], h, l);
+        *reinterpret_cast<uint32_t*>(ph) = h;
+        *reinterpret_cast<uint32_t*>(pl) = l;
+        ph += plane;
+        pl += plane;
+      }
+    }
+    __syncthreads();          // all reads of this buffer done before the cp.async of segment seg+2 lands in it
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 struct WinoOutParams {
   const float* m; int64_t Mtot;
   int B, H, W, Cout, th, tw;
@@ -354,9 +487,19 @@ int bbdm_wino_input(const BbdmWinoInputArgs* a, void* stream) {
   p.raw_hi = (__nv_bfloat16*)a->raw_hi; p.raw_lo = (__nv_bfloat16*)a->raw_lo;
   const int64_t ctas = (int64_t)p.B * p.th;
   BBDM_REQUIRE(ctas < (1ll << 31), "wino_input: too many tile rows");
-  static int vec = 0;       // BBDM_WINO_IN_VEC=1|2: channels per thread (A/B switch; default 1)
-  if (!vec) { const char* e = getenv("BBDM_WINO_IN_VEC"); vec = (e && atoi(e) == 2) ? 2 : 1; }
-  if (vec == 2) {
+  // default: the shared-memory staged kernel (needs 64-channel chunks inside one source tensor);
+  // BBDM_WINO_IN_VEC=1|2 selects the register-only variant with 1 or 2 channels per thread (fallback / A-B switch)
+  static int vec = -1;
+  if (vec < 0) { const char* e = getenv("BBDM_WINO_IN_VEC"); vec = e ? (atoi(e) == 2 ? 2 : 1) : 0; }
+  if (vec == 0 && p.c1 % WI_CC == 0 && p.c2 % WI_CC == 0) {
+    static DeviceOnce configured;
+    if (configured.need()) {
+      BBDM_CUDA_CHECK(cudaFuncSetAttribute(wino_input_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WI_SMEM));
+      configured.mark();
+    }
+    dim3 grid((unsigned)ctas, p.C / WI_CC);
+    wino_input_smem_kernel<<<grid, 256, WI_SMEM, (cudaStream_t)stream>>>(p);
+  } else if (vec == 2 || (vec == 0 && p.c1 % 2 == 0 && p.c2 % 2 == 0)) {
     dim3 grid((unsigned)ctas, (p.C / 2 + 255) / 256);
     wino_input_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   } else {

@@ -80,6 +80,9 @@ class KernelExecutor:
         # (parity mode only; below that the transform traffic outweighs the 4x MAC saving).  BBDM_WINOGRAD=0 disables.
         self.wino = precision == "split3" and os.environ.get("BBDM_WINOGRAD", "1") != "0"
         self.wino_min_c = int(os.environ.get("BBDM_WINO_MIN_C", "256"))
+        # ... and at least this many 4x4 tiles per launch: below it the 36 position GEMMs have too few M tiles each
+        # (measured: cfg1, 256 tiles, graph replay 3.9 -> 4.4 ms with Winograd; cfg3, 2048 tiles, 20.2 -> 17.1 ms)
+        self.wino_min_tiles = int(os.environ.get("BBDM_WINO_MIN_TILES", "512"))
         self._wino_geom = {}
 
     def _umma_ok(self, cin, cout, w):
@@ -173,7 +176,12 @@ class KernelExecutor:
         return g
 
     def _wino_ok(self, ent, B, H, W):
-        return bool(self.wino and "u_hi" in ent and self._wino_geometry(B, H, W)[3])
+        if not (self.wino and "u_hi" in ent):
+            return False
+        # >= 128 tiles per image: always (the choice must not depend on the batch size there -- batch-size independent,
+        # bit-identical results at the pixel resolutions); smaller maps: only when the whole batch has enough tiles
+        th, tw, tiles, ok = self._wino_geometry(B, H, W)
+        return bool(ok and (th * tw >= 128 or tiles >= self.wino_min_tiles))
 
     def _wino_conv(self, pool, ent, src1, src2, *, mean, rstd, gamma, beta, film=None, silu=True, raw=None,
                    residual=None, res_mode=cabi.RES_NONE, stats=True):

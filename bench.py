@@ -73,6 +73,20 @@ CONFIGS = {
 }
 METRIC = "denoising-steps/sec (UNet fwd) at 256^2 pixel-BBDM"
 
+# VQGAN ends of the latent configs (Template-LBBDM-f4/f8/f16.yaml ddconfigs; cfg4 / cfg5 are the scaled variants of
+# f8 at 512^2 -> 64x64x4, f16 at 1024^2 -> 64x64x16), random init (ckpt_path None)
+VQGAN_ENDS = {
+    "cfg3": dict(image=256, embed_dim=3, n_embed=8192,
+                 ddconfig=dict(double_z=False, z_channels=3, resolution=256, in_channels=3, out_ch=3, ch=128,
+                               ch_mult=(1, 2, 4), num_res_blocks=2, attn_resolutions=[], dropout=0.0)),
+    "cfg4": dict(image=512, embed_dim=4, n_embed=16384,
+                 ddconfig=dict(double_z=False, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
+                               ch_mult=(1, 2, 2, 4), num_res_blocks=2, attn_resolutions=[32], dropout=0.0)),
+    "cfg5": dict(image=1024, embed_dim=16, n_embed=16384,
+                 ddconfig=dict(double_z=False, z_channels=16, resolution=256, in_channels=3, out_ch=3, ch=128,
+                               ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, attn_resolutions=[16], dropout=0.0)),
+}
+
 
 def namespace(unet, sample_step):
     import argparse as ap
@@ -217,6 +231,113 @@ def run_reference_arm(args, cfg):
 
 
 # ------------------------------------------------------------------------------------------
+def run_ends(args, cfg):
+    """End-to-end LBBDM sampling (BASELINE configs[2..4]): images -> VQGAN encode -> the full skip-sampling loop
+    (one captured CUDA graph per step) -> quantize + VQGAN decode -> images, through
+    LatentBrownianBridgeModel.sample() -- the call BBDMRunner.sample_to_eval makes (BBDMRunner.py:240) -- with the
+    condition batch coming from pinned host memory and the result copied back inside the timed region.
+    value = sample_step * batches / time, i.e. the same denoising-steps/s metric with both ends included."""
+    import argparse as ap
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from bbdm_b200 import cabi
+    from model.BrownianBridge.LatentBrownianBridgeModel import LatentBrownianBridgeModel
+    vq = VQGAN_ENDS[args.config]
+    ns = namespace(cfg["unet"], cfg["sample_step"])
+    ns.VQGAN = ap.Namespace(params=ap.Namespace(ckpt_path=None, embed_dim=vq["embed_dim"], n_embed=vq["n_embed"],
+                                                ddconfig=ap.Namespace(**vq["ddconfig"]),
+                                                lossconfig=ap.Namespace(target="torch.nn.Identity")))
+    net = LatentBrownianBridgeModel(ns).eval()
+    init_weights(net.denoise_fn)
+    torch.manual_seed(4321)
+    with torch.no_grad():
+        for n, p in net.vqgan.named_parameters():
+            if p.dim() >= 2:
+                p.normal_(0, 0.02)
+        net.vqgan.quantize.embedding.weight.normal_(0, 0.5)
+    net = net.to(dev)
+    B, S = cfg["batch"], vq["image"]
+    xc_host = synth((B, 3, S, S), 3000 + rank).pin_memory()
+    out_host = torch.empty((B, 3, S, S)).pin_memory()
+
+    def one_batch():
+        xc = xc_host.to(dev, non_blocking=True)
+        img = net.sample(xc, clip_denoised=False)
+        out_host.copy_(img, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    import contextlib
+    import io
+    with contextlib.redirect_stderr(io.StringIO()):            # tqdm bars of the loop
+        one_batch()                                            # warm-up: weight packing, pools, graph capture
+        barrier()
+        clocks = ClockSampler(local)
+        clocks.start()
+        time.sleep(0.3)
+        n0 = cabi.LAUNCHES["n"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        barrier()
+        e0.record()
+        for _ in range(args.batches):
+            one_batch()
+        e1.record()
+        barrier()
+        clk = clocks.stop(t0, time.time())
+    ms = e0.elapsed_time(e1) / args.batches
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    net._bridge.backend().check_fault()
+    # the ends alone (same tensors), for the breakdown
+    xc = xc_host.to(dev)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    with torch.no_grad():
+        z = net.encode(xc, cond=True)
+        net.decode(z, cond=False)
+        torch.cuda.synchronize()
+        e[0].record()
+        z = net.encode(xc, cond=True)
+        e[1].record()
+        net.decode(z, cond=False)
+        e[2].record()
+    torch.cuda.synchronize()
+    n_steps = cfg["sample_step"]
+    if rank == 0:
+        nbytes = B * 3 * S * S * 4
+        val = world * n_steps * 1e3 / ms
+        line = {"metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": world, "steps": n_steps * args.batches,
+                "warmup": n_steps, "ms_per_step": ms / n_steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16x3 / fp16x3 split tensor-core products, fp32 accumulate (fp32-class)",
+                "data": "synthetic",
+                "config": {"workload": cfg["name"] + " -- END TO END through LatentBrownianBridgeModel.sample(): VQGAN encode + "
+                                       f"{n_steps}-step loop + quantize/decode, images {S}x{S}", "batch_per_gpu": B,
+                           "parallelism": f"dp{world} (sharded sampling, no collective)",
+                           "ms_per_batch": ms, "encode_ms": e[0].elapsed_time(e[1]), "decode_ms": e[1].elapsed_time(e[2]),
+                           "loop_ms": ms - e[0].elapsed_time(e[2]), "images_per_s": world * B * 1e3 / ms},
+                "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": nbytes / n_steps,
+                        "d2h_bytes_per_step": nbytes / n_steps, "ms_per_step": ms / n_steps,
+                        "note": "host images in, host images out, per sampled batch (bytes amortised over the loop's steps)"},
+                "gpu_launches": (cabi.LAUNCHES["n"] - n0), "clocks": clk}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -228,10 +349,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-convs", default=None, help="write per-conv-launch shape/time/TFLOPs (profiled step) to this file")
     ap.add_argument("--graph", action="store_true", help="also time CUDA-graph replays of the captured sampling step")
+    ap.add_argument("--ends", action="store_true", help="latent configs: end-to-end sample() incl. VQGAN encode / decode")
+    ap.add_argument("--batches", type=int, default=1, help="--ends: sampled batches in the timed region")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
         return run_reference_arm(args, cfg)
+    if args.ends:
+        assert args.config in VQGAN_ENDS, "--ends needs a latent config (cfg3, cfg4, cfg5)"
+        return run_ends(args, cfg)
     assert args.warmup >= 3, "timing rules: W >= 3"
 
     rank = int(os.environ.get("RANK", "0"))

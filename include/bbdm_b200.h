@@ -351,6 +351,41 @@ int bbdm_gn_bwd_apply(const float* x, const float* da, int B, int H, int W, int 
                       const float* s1, const float* s2, float* dx, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Output path of sample_to_eval
+ * ------------------------------------------------------------------------------------------ */
+
+/* images [B,C,H,W] fp32 -> out [B,H,W,C] uint8: clamp(x*0.5+0.5, 0, 1) (if to_normal), then
+ * clamp(x*255+0.5, 0, 255) truncated to uint8 -- the per-image expression of save_single_image
+ * (runners/utils.py:67-74: mul_(0.5).add_(0.5).clamp_(0,1).mul_(255).add_(0.5).clamp_(0,255).permute(1,2,0)
+ * .to(uint8)), same operation order => byte-exact, for the whole batch in one launch. */
+int bbdm_denorm_to_uint8(const float* images, int B, int C, int H, int W, int to_normal, uint8_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-tensor optimizer / EMA updates: one launch over every parameter tensor.
+ * params/grads: DEVICE arrays of n tensor pointers (fp32; a NULL gradient skips that tensor like torch does);
+ * numel/state_off: DEVICE int64 [n] (elements, offset of the tensor's state inside the flat exp_avg / exp_avg_sq /
+ * shadow buffers); chunk_tensor/chunk_index: DEVICE int32 [n_chunks], one entry per CTA = (tensor, chunk of
+ * bbdm_optim_chunk_elems() elements).
+ * ------------------------------------------------------------------------------------------ */
+int bbdm_optim_chunk_elems(void);
+
+/* torch.optim.Adam's update (the optimizer runners/utils.py:48-57 builds, stepped at runners/BaseRunner.py:413),
+ * non-amsgrad, L2 weight decay, `step` = the 1-based step count of this update (bias corrections computed in fp64 as
+ * torch does).  ema_shadow != NULL additionally applies shadow = (1-ema_decay)*p_new + ema_decay*shadow in the same
+ * pass (runners/base/EMA.py:21-29 with with_decay=True). */
+int bbdm_adam_multi(void* const* params, const void* const* grads, const int64_t* numel, const int64_t* state_off,
+                    const int32_t* chunk_tensor, const int32_t* chunk_index, int n_chunks, float* exp_avg,
+                    float* exp_avg_sq, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                    float* ema_shadow, double ema_decay, void* stream);
+
+/* EMA.update (runners/base/EMA.py:21-29): shadow = (1-decay)*param + decay*shadow (the reference's operation
+ * order with the python-float scalars (1.0 - decay) and decay each rounded to fp32: bit-exact), or shadow = param
+ * when with_decay == 0.  decay is a double like the python attribute. */
+int bbdm_ema_multi(const void* const* params, const int64_t* numel, const int64_t* state_off,
+                   const int32_t* chunk_tensor, const int32_t* chunk_index, int n_chunks, float* shadow, double decay,
+                   int with_decay, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Attention core
  * ------------------------------------------------------------------------------------------ */
 

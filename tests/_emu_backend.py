@@ -262,6 +262,38 @@ class EmuBackend:
             sp[:, 0, :, 1] = (o.reshape(B, -1, Cout) ** 2).sum(1)
         out.copy_(o)
 
+    def denorm_to_uint8(self, images, to_normal, out):
+        self.calls.append("denorm_to_uint8")
+        x = images.detach().clone()
+        if to_normal:
+            x = x.mul_(0.5).add_(0.5).clamp_(0, 1.)
+        out.copy_(x.mul_(255).add_(0.5).clamp_(0, 255).permute(0, 2, 3, 1).to(torch.uint8))
+
+    # -- multi-tensor optimizer / EMA (flat state buffers) ----------------------------------------------------
+    def optim_chunk_elems(self):
+        return 4096
+
+    def adam_multi(self, tab, exp_avg, exp_avg_sq, *, lr, beta1, beta2, eps, weight_decay, step, ema_shadow=None,
+                   ema_decay=0.0):
+        self.calls.append("adam_multi")
+        bc1, bc2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
+        for p, m, v, s in zip(tab.tensors, tab.views(exp_avg), tab.views(exp_avg_sq),
+                              tab.views(ema_shadow) if ema_shadow is not None else [None] * len(tab.tensors)):
+            if p.grad is None:
+                continue
+            g = p.grad + weight_decay * p.data if weight_decay else p.grad
+            m.lerp_(g, 1.0 - beta1)
+            v.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+            denom = (v.sqrt() / (bc2 ** 0.5)).add_(eps)
+            p.data.addcdiv_(m, denom, value=-(lr / bc1))
+            if s is not None:
+                s.copy_((1.0 - ema_decay) * p.data + ema_decay * s)
+
+    def ema_multi(self, tab, shadow, decay, with_decay=True):
+        self.calls.append("ema_multi")
+        for p, s in zip(tab.tensors, tab.views(shadow)):
+            s.copy_((1.0 - decay) * p.data + decay * s if with_decay else p.data)
+
     def pack_weight_split_taps(self, w, hi, lo):
         self.calls.append("pack_weight_split_taps")
         self._write_split(w.permute(2, 0, 1), hi, lo)

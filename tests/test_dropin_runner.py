@@ -31,12 +31,16 @@ def test_unmodified_bbdm_runner_trains_and_samples(tmp_path, monkeypatch):
     conftest.install_reference_shims()
     from bbdm_b200.bridge import BridgeOps
     monkeypatch.setattr(BridgeOps, "backend_factory", staticmethod(lambda: EmuBackend()))
+    from bbdm_b200.optim import FusedEMA
+    monkeypatch.setattr(FusedEMA, "backend_factory", staticmethod(lambda: EmuBackend()))   # runners.base.EMA overlay
     # reference modules, untouched
     from utils import dict2namespace, get_runner
     import model.BrownianBridge.BrownianBridgeModel as overlay
     import runners.DiffusionBasedModelRunners.BBDMRunner as runner_mod
     assert overlay.__file__.startswith(conftest.REPO)                 # model classes: this repo
     assert runner_mod.__file__.startswith(conftest.REF)               # runner: the reference
+    import runners.base.EMA as ema_mod
+    assert ema_mod.__file__.startswith(conftest.REPO) and ema_mod.EMA is FusedEMA   # EMA: this repo's overlay
     assert runner_mod.BrownianBridgeModel is overlay.BrownianBridgeModel
 
     with open(os.path.join(conftest.REF, "configs", "Template-BBDM.yaml")) as f:

@@ -55,7 +55,7 @@ def test_winograd_path_wiring_matches_reference_fixture():
     be = EmuBackend()
     eng = UNetEngine(net, backend=be)
     assert eng.wino
-    eng.wino_min_c = 64
+    eng.wino_min_c, eng.wino_min_tiles = 64, 128
     out = eng.forward(g["x"], g["t"], g["y"])
     assert be.calls.count("wino_input") >= 4 and be.calls.count("wino_input") == be.calls.count("wino_output")
     assert not torch.isnan(out).any()

@@ -387,3 +387,80 @@ def test_attention_tc(be, B, T, heads, order):
     assert rel_dev(out, want) < 2e-5, rel_dev(out, want)
     h, l = O.bf16_split(out.cpu())
     assert torch.equal(oh.float().cpu(), h) and torch.equal(ol.float().cpu(), l)
+
+
+# ------------------------------------------------------------------------------------ optimizer / EMA
+def test_fused_adam_and_ema_match_torch_over_10_steps():
+    """bbdm_adam_multi / bbdm_ema_multi (one launch over all tensors) against torch.optim.Adam and the reference EMA
+    expression on the same gradients: 10 steps, odd tensor sizes, weight decay."""
+    import torch.nn as nn
+    from bbdm_b200.optim import FusedAdam, FusedEMA
+
+    def make():
+        torch.manual_seed(3)
+        return nn.ParameterList([nn.Parameter(torch.randn(s, device=DEV) * 0.1) for s in
+                                 [(128, 64, 3, 3), (513,), (7, 5), (1,), (1024, 333), (64,)]])
+    pa, pb = make(), make()
+    oa = torch.optim.Adam(pa, lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-3)
+    ob = FusedAdam(pb, lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-3)
+    ema = FusedEMA(0.995)
+    holder = nn.Module()
+    holder.p = pb
+    ema.register(holder)
+    shadow_ref = [p.data.clone() for p in pa]
+    g = torch.Generator(device=DEV).manual_seed(5)
+    for it in range(10):
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            gr = torch.randn(a.shape, device=DEV, generator=g)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        oa.step()
+        if it % 2:
+            ob.step(ema=ema, ema_update=True)                 # EMA fused into the Adam pass
+        else:
+            ob.step()
+            ema.update(holder, with_decay=True)               # separate EMA launch
+        shadow_ref = [(1.0 - 0.995) * p.data + 0.995 * s for p, s in zip(pa, shadow_ref)]
+    for a, b in zip(pa, pb):
+        assert rel_dev(b, a) < 2e-6, rel_dev(b, a)
+    for (n, s), r in zip(ema.shadow.items(), shadow_ref):
+        assert rel_dev(s, r) < 2e-6, rel_dev(s, r)
+    pb[2].grad = None                      # a parameter without gradient: per-parameter step counts are not kept
+    with pytest.raises(NotImplementedError):
+        ob.step()
+    sa, sb = oa.state_dict()["state"], ob.state_dict()["state"]
+    for k in sa:      # (a one-element tensor can sit near zero: absolute floor at 1e-6 of the gradient scale)
+        for f in ("exp_avg", "exp_avg_sq"):
+            assert torch.allclose(sb[k][f], sa[k][f], rtol=1e-5, atol=1e-6), (k, f, rel_dev(sb[k][f], sa[k][f]))
+
+
+def test_ema_update_bit_exact_vs_reference_expression():
+    import torch.nn as nn
+    from bbdm_b200.optim import FusedEMA
+    net = nn.Sequential(nn.Conv2d(16, 32, 3), nn.Linear(77, 13)).to(DEV)
+    ema = FusedEMA(0.999)
+    ema.register(net)
+    ref = {n: p.data.clone() for n, p in net.named_parameters()}
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(torch.randn_like(p) * 0.01)
+    ema.update(net)
+    for n, p in net.named_parameters():
+        assert torch.equal(ema.shadow[n], (1.0 - 0.999) * p.data + 0.999 * ref[n])      # runners/base/EMA.py:26
+
+
+# ------------------------------------------------------------------------------------ sample_to_eval output path
+@pytest.mark.parametrize("to_normal", [True, False])
+def test_denorm_to_uint8_byte_exact(be, to_normal):
+    """bbdm_denorm_to_uint8 against the reference's per-image expression (runners/utils.py:67-74), including values
+    outside [-1, 1] and exact rounding boundaries."""
+    x = rnd((4, 3, 37, 29), 90, 0.8)
+    x[0, 0, 0, :8] = torch.tensor([-1.0, 1.0, 0.0, -1.5, 1.5, 0.00392157, -0.00392157, 0.99607843])
+    if not to_normal:
+        x = x * 0.5 + 0.5
+    out = torch.empty((4, 37, 29, 3), dtype=torch.uint8, device=DEV)
+    be.denorm_to_uint8(x.to(DEV), to_normal, out)
+    ref = x.clone()
+    if to_normal:
+        ref = ref.mul_(0.5).add_(0.5).clamp_(0, 1.)
+    ref = ref.mul_(255).add_(0.5).clamp_(0, 255).permute(0, 2, 3, 1).to(torch.uint8)
+    assert torch.equal(out.cpu(), ref)
