@@ -72,7 +72,8 @@ class WinoInputArgs(C.Structure):
                 ("mean", C.c_void_p), ("rstd", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
                 ("film_scale", C.c_void_p), ("film_shift", C.c_void_p), ("film_stride", C.c_int64),
                 ("silu", C.c_int),
-                ("v_hi", C.c_void_p), ("v_lo", C.c_void_p), ("raw_hi", C.c_void_p), ("raw_lo", C.c_void_p)]
+                ("v_hi", C.c_void_p), ("v_lo", C.c_void_p), ("raw_hi", C.c_void_p), ("raw_lo", C.c_void_p),
+                ("act_hi", C.c_void_p), ("act_lo", C.c_void_p)]
 
 
 class WinoOutputArgs(C.Structure):
@@ -139,7 +140,7 @@ def load():
     lib.bbdm_wino_geometry.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i), C.POINTER(i64), C.POINTER(i)]
     lib.bbdm_wino_input.argtypes = [C.POINTER(WinoInputArgs), vp]
     lib.bbdm_wino_output.argtypes = [C.POINTER(WinoOutputArgs), vp]
-    lib.bbdm_wino_pack_weight.argtypes = [vp, i, i, vp, vp, vp]
+    lib.bbdm_wino_pack_weight.argtypes = [vp, i, i, i, vp, vp, vp]
     lib.bbdm_denorm_to_uint8.argtypes = [vp, i, i, i, i, i, vp, vp]
     lib.bbdm_optim_chunk_elems.argtypes = []
     lib.bbdm_adam_multi.argtypes = [vp, vp, vp, vp, vp, vp, i, vp, vp, f, f, f, f, f, i64, vp, C.c_double, vp]
@@ -355,13 +356,14 @@ class CudaBackend:
         check(self.lib.bbdm_wino_geometry(B, H, W, C.byref(th), C.byref(tw), C.byref(tot), C.byref(el)))
         return th.value, tw.value, tot.value, bool(el.value)
 
-    def wino_input(self, src1, src2, *, groups, mean, rstd, gamma, beta, film_scale=None, film_shift=None,
-                   film_stride=0, silu=True, v_hi, v_lo, raw_hi=None, raw_lo=None):
+    def wino_input(self, src1, src2, *, groups=32, mean=None, rstd=None, gamma=None, beta=None, film_scale=None,
+                   film_shift=None, film_stride=0, silu=True, v_hi, v_lo, raw_hi=None, raw_lo=None, act_hi=None,
+                   act_lo=None):
         B, H, W, c1 = src1.shape
         a = WinoInputArgs(ptr(_req(src1)), c1, ptr(src2), 0 if src2 is None else src2.shape[3], B, H, W, groups,
                           ptr(mean), ptr(rstd), ptr(gamma), ptr(beta), ptr(film_scale), ptr(film_shift), film_stride,
                           int(silu), ptr(_req(v_hi, torch.float16)), ptr(_req(v_lo, torch.float16)),
-                          ptr(raw_hi), ptr(raw_lo))
+                          ptr(raw_hi), ptr(raw_lo), ptr(act_hi), ptr(act_lo))
         check(self.lib.bbdm_wino_input(C.byref(a), stream()))
         LAUNCHES["n"] += 1
 
@@ -371,10 +373,11 @@ class CudaBackend:
         check(self.lib.bbdm_wino_output(C.byref(a), stream()))
         LAUNCHES["n"] += 1
 
-    def wino_pack_weight(self, w, u_hi, u_lo):
-        """w [Cout,Cin,3,3] fp32 -> u_hi/u_lo fp16 [36, Cout, Cin] (2^8 * G w G^T)."""
+    def wino_pack_weight(self, w, u_hi, u_lo, dgrad=False):
+        """w [Cout,Cin,3,3] fp32 -> u_hi/u_lo fp16 [36, Cout, Cin] (2^8 * G w G^T); dgrad: [36, Cin, Cout] of the
+        flipped / channel-swapped kernel."""
         Cout, Cin = w.shape[0], w.shape[1]
-        check(self.lib.bbdm_wino_pack_weight(ptr(_req(w)), Cout, Cin, ptr(_req(u_hi, torch.float16)),
+        check(self.lib.bbdm_wino_pack_weight(ptr(_req(w)), Cout, Cin, int(dgrad), ptr(_req(u_hi, torch.float16)),
                                              ptr(_req(u_lo, torch.float16)), stream()))
         LAUNCHES["n"] += 1
 

@@ -115,6 +115,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
   __shared__ __align__(8) uint64_t bars[2 * 8 + 4];
   __shared__ uint32_t tmem_base_s;
   __shared__ int abort_s;
+  // per-epilogue-warp staging tile (32 rows x 16 columns, row stride 20 floats) for the coalesced plain store
+  __shared__ __align__(16) float stg_s[Cfg::EPI_WARPS][32 * 20];
 
   const uint32_t tiles_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -273,6 +275,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
       const int64_t pix = ((int64_t)bb * OH + hh) * OW + ww;
       const int n0 = nb * BN + col0;
 
+      // plain GEMM-style output (no bias / residual / statistics / split copy: the Winograd position GEMMs): the tile
+      // is stored through a shared-memory transpose, 8 rows x 64 contiguous bytes per instruction, instead of one
+      // 16-byte piece of 32 different rows (half-used sectors; for K = 512 tiles the store took longer than the two
+      // chunks the tensor core may run ahead)
+      const bool plain = p.out != nullptr && p.bias == nullptr && p.bias2 == nullptr && p.res_mode == BBDM_RES_NONE &&
+                         p.out_hi == nullptr && p.stats == nullptr && p.out_nchw_c == 0;
+      int64_t prow[4];
+      bool pval[4];
+      if (plain) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int src = 8 * i + (lane >> 2);
+          prow[i] = __shfl_sync(0xffffffffu, pix, src);
+          pval[i] = __shfl_sync(0xffffffffu, valid ? 1 : 0, src) != 0;
+        }
+      }
       float racc[COLS];
 #pragma unroll
       for (int j = 0; j < COLS; ++j) racc[j] = 0.f;
@@ -300,6 +318,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         for (int ch = 0; ch < COLS / 32; ++ch) {
           const int nc = n0 + ch * 32;
           float* r = &racc[ch * 32];
+          if (plain) {
+            float* st = stg_s[ew];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(st + lane * 20 + 4 * j) =
+                    make_float4(r[16 * h + 4 * j], r[16 * h + 4 * j + 1], r[16 * h + 4 * j + 2], r[16 * h + 4 * j + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 v = *reinterpret_cast<const float4*>(st + (8 * i + (lane >> 2)) * 20 + (lane & 3) * 4);
+                if (pval[i]) st_f4(p.out + prow[i] * p.Cout + nc + 16 * h + (lane & 3) * 4, v);
+              }
+              __syncwarp();
+            }
+            continue;
+          }
           if (valid) {
           if (p.bias) {
 #pragma unroll

@@ -70,6 +70,7 @@ struct WinoInParams {
   int silu;
   __half* v_hi; __half* v_lo;
   __nv_bfloat16* raw_hi; __nv_bfloat16* raw_lo;
+  __nv_bfloat16* act_hi; __nv_bfloat16* act_lo;   // optional split-bf16 planes of the ACTIVATED tensor (wgrad operand)
 };
 
 // One CTA per (sample b, tile row ty, chunk of 256*VEC channels): every thread owns VEC channels and walks the tile
@@ -227,14 +228,17 @@ wino_input_smem_kernel(const WinoInParams p) {
   float sc[4], sh[4];
 #pragma unroll
   for (int v = 0; v < 4; ++v) {
-    const int c = cbase + ch4 * 4 + v;
-    const int g = c / p.cpg;
-    const float s0 = p.rstd[b * p.groups + g] * p.gamma[c];
-    const float h0 = p.beta[c] - p.mean[b * p.groups + g] * s0;
-    float f1 = 1.0f, f0 = 0.0f;
-    if (p.fscale) { f1 = 1.0f + p.fscale[(int64_t)b * p.fstride + c]; f0 = p.fshift[(int64_t)b * p.fstride + c]; }
-    sc[v] = s0 * f1;
-    sh[v] = fmaf(h0, f1, f0);
+    sc[v] = 1.0f; sh[v] = 0.0f;            // mean == nullptr: identity (the data-gradient conv transforms dY as is)
+    if (p.mean) {
+      const int c = cbase + ch4 * 4 + v;
+      const int g = c / p.cpg;
+      const float s0 = p.rstd[b * p.groups + g] * p.gamma[c];
+      const float h0 = p.beta[c] - p.mean[b * p.groups + g] * s0;
+      float f1 = 1.0f, f0 = 0.0f;
+      if (p.fscale) { f1 = 1.0f + p.fscale[(int64_t)b * p.fstride + c]; f0 = p.fshift[(int64_t)b * p.fstride + c]; }
+      sc[v] = s0 * f1;
+      sh[v] = fmaf(h0, f1, f0);
+    }
   }
   const int nseg = (p.tw + WI_TX - 1) / WI_TX;
   const uint32_t patch_s = (uint32_t)__cvta_generic_to_shared(patch);
@@ -284,6 +288,14 @@ wino_input_smem_kernel(const WinoInParams p) {
         if (p.silu) {
           a.x = __fdividef(a.x, 1.0f + __expf(-a.x)); a.y = __fdividef(a.y, 1.0f + __expf(-a.y));
           a.z = __fdividef(a.z, 1.0f + __expf(-a.z)); a.w = __fdividef(a.w, 1.0f + __expf(-a.w));
+        }
+        if (p.act_hi && i >= 1 && i <= 4 && j >= 1 && j <= 4 * WI_TX) {
+          // training: the activated tensor's split-bf16 planes are the weight-gradient GEMM's operand
+          uint2 h, l;
+          split4(a, h, l);
+          const int64_t off = (((int64_t)b * p.H + iy) * p.W + ix) * p.C + cbase + ch4 * 4;
+          *reinterpret_cast<uint2*>(p.act_hi + off) = h;
+          *reinterpret_cast<uint2*>(p.act_lo + off) = l;
         }
       }
       *q = a;                                              // out of the image: exact zero (padding of the activation)
@@ -405,13 +417,21 @@ wino_output_kernel(const WinoOutParams p) {
 
 // ------------------------------------------------------------------------------------------
 // U[q][co][ci] = 2^8 * (G g G^T)[q] in fp64, split into fp16 planes.  One thread per (co, ci).
+// dgrad != 0: the data-gradient conv's weights instead -- kernel flipped, channels swapped: U[q][ci][co] from
+// g'[ky][kx] = w[co][ci][2-ky][2-kx] (threads run over co fastest so the stores stay coalesced).
 __global__ void __launch_bounds__(256)
-wino_weight_kernel(const float* __restrict__ w, int Cout, int Cin, __half* __restrict__ u_hi, __half* __restrict__ u_lo) {
+wino_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int dgrad, __half* __restrict__ u_hi,
+                   __half* __restrict__ u_lo) {
   const int64_t n = (int64_t)Cout * Cin;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
     double g[3][3], t[6][3];
+    int64_t src = idx;
+    if (dgrad) { const int64_t ci = idx / Cout, co = idx - ci * Cout; src = co * Cin + ci; }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) g[i / 3][i % 3] = (double)w[idx * 9 + i];
+    for (int i = 0; i < 9; ++i) {
+      const int k = dgrad ? 8 - i : i;
+      g[i / 3][i % 3] = (double)w[src * 9 + k];
+    }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const double g0 = g[0][j], g1 = g[1][j], g2 = g[2][j];
@@ -473,8 +493,13 @@ int bbdm_wino_input(const BbdmWinoInputArgs* a, void* stream) {
   p.groups = a->groups;
   BBDM_REQUIRE(p.B > 0 && p.H > 0 && p.W > 0 && p.H % 4 == 0 && p.W % 4 == 0, "wino_input: H, W must be multiples of 4");
   BBDM_REQUIRE(p.c1 % 2 == 0 && p.c2 % 2 == 0 && p.C > 0, "wino_input: channel counts must be even");
-  BBDM_REQUIRE(a->mean && a->rstd && a->gamma && a->beta && p.groups > 0 && p.C % p.groups == 0,
-               "wino_input: incomplete GroupNorm args");
+  if (a->mean) {
+    BBDM_REQUIRE(a->rstd && a->gamma && a->beta && p.groups > 0 && p.C % p.groups == 0, "wino_input: incomplete GroupNorm args");
+  } else {
+    BBDM_REQUIRE(!a->silu && !a->film_scale, "wino_input: identity mode (mean == NULL) takes no activation / FiLM");
+    if (p.groups <= 0) p.groups = 1;
+  }
+  BBDM_REQUIRE((a->act_hi == nullptr) == (a->act_lo == nullptr), "wino_input: act hi/lo must come in pairs");
   BBDM_REQUIRE((a->film_scale == nullptr) == (a->film_shift == nullptr), "wino_input: film scale/shift mismatch");
   BBDM_REQUIRE((a->raw_hi == nullptr) == (a->raw_lo == nullptr), "wino_input: raw hi/lo must come in pairs");
   p.cpg = p.C / p.groups;
@@ -485,6 +510,8 @@ int bbdm_wino_input(const BbdmWinoInputArgs* a, void* stream) {
   p.silu = a->silu;
   p.v_hi = (__half*)a->v_hi; p.v_lo = (__half*)a->v_lo;
   p.raw_hi = (__nv_bfloat16*)a->raw_hi; p.raw_lo = (__nv_bfloat16*)a->raw_lo;
+  p.act_hi = (__nv_bfloat16*)a->act_hi; p.act_lo = (__nv_bfloat16*)a->act_lo;
+  const bool smem_only = a->mean == nullptr || a->act_hi != nullptr;      // features only the staged kernel has
   const int64_t ctas = (int64_t)p.B * p.th;
   BBDM_REQUIRE(ctas < (1ll << 31), "wino_input: too many tile rows");
   // default: the shared-memory staged kernel (needs 64-channel chunks inside one source tensor);
@@ -499,6 +526,8 @@ int bbdm_wino_input(const BbdmWinoInputArgs* a, void* stream) {
     }
     dim3 grid((unsigned)ctas, p.C / WI_CC);
     wino_input_smem_kernel<<<grid, 256, WI_SMEM, (cudaStream_t)stream>>>(p);
+  } else if (smem_only) {
+    BBDM_REQUIRE(false, "wino_input: identity mode / act planes need channel counts that are multiples of 64");
   } else if (vec == 2 || (vec == 0 && p.c1 % 2 == 0 && p.c2 % 2 == 0)) {
     dim3 grid((unsigned)ctas, (p.C / 2 + 255) / 256);
     wino_input_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
@@ -531,12 +560,12 @@ int bbdm_wino_output(const BbdmWinoOutputArgs* a, void* stream) {
   return BBDM_OK;
 }
 
-int bbdm_wino_pack_weight(const float* w, int Cout, int Cin, void* u_hi, void* u_lo, void* stream) {
+int bbdm_wino_pack_weight(const float* w, int Cout, int Cin, int dgrad, void* u_hi, void* u_lo, void* stream) {
   BBDM_REQUIRE(w && u_hi && u_lo && Cout > 0 && Cin > 0, "wino_pack_weight: bad args");
   const int64_t n = (int64_t)Cout * Cin;
   int64_t g = (n + 255) / 256;
   if (g > (int64_t)num_sms() * 16) g = (int64_t)num_sms() * 16;
-  wino_weight_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, (__half*)u_hi, (__half*)u_lo);
+  wino_weight_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, dgrad, (__half*)u_hi, (__half*)u_lo);
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
 }

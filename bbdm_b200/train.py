@@ -14,11 +14,50 @@ DDP's bucketed NCCL allreduce works unchanged.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import cabi
 
 _BACKEND = None
+
+# Winograd F(4x4,3x3) for the forward and data-gradient 3x3 convolutions of the training graph (csrc/winograd.cu;
+# same eligibility rule as the sampling engine).  The weight gradient stays the direct tcgen05 GEMM.
+WINO_TRAIN = os.environ.get("BBDM_WINOGRAD_TRAIN", "1") != "0"
+WINO_MIN_C = int(os.environ.get("BBDM_WINO_MIN_C", "256"))
+WINO_MIN_TILES = int(os.environ.get("BBDM_WINO_MIN_TILES", "512"))
+
+
+def _wino_ok(be, B, H, W, Cin, Cout, k):
+    if not WINO_TRAIN or k != 3 or min(Cin, Cout) < WINO_MIN_C or Cin % 64 or Cout % 64 or not hasattr(be, "wino_geometry"):
+        return False
+    th, tw, tiles, ok = be.wino_geometry(B, H, W)
+    return bool(ok and (th * tw >= 128 or tiles >= WINO_MIN_TILES))
+
+
+def _wino_conv(be, xn, weight, *, dgrad, gn=None, act_planes=None, bias=None, residual=None, out_channels):
+    """3x3 conv of the NHWC tensor xn on the Winograd path: input transform (GroupNorm affine + FiLM + SiLU fused when
+    gn = dict(mean, rstd, gamma, beta, film_scale, film_shift, film_stride, silu); identity for gn None), 36
+    position GEMMs, output transform (+ bias + residual).  dgrad: use the flipped / channel-swapped kernel."""
+    B, H, W, C = xn.shape
+    dev = xn.device
+    _, _, mt, _ = be.wino_geometry(B, H, W)
+    v_hi = torch.empty((36, mt, C), dtype=torch.float16, device=dev)
+    v_lo = torch.empty_like(v_hi)
+    kw = dict(silu=False) if gn is None else gn
+    akw = {} if act_planes is None else dict(act_hi=act_planes[0], act_lo=act_planes[1])
+    be.wino_input(xn, None, v_hi=v_hi, v_lo=v_lo, **kw, **akw)
+    u_hi = torch.empty((36, out_channels, C), dtype=torch.float16, device=dev)
+    u_lo = torch.empty_like(u_hi)
+    be.wino_pack_weight(weight.detach().contiguous(), u_hi, u_lo, dgrad=dgrad)
+    m = torch.empty((36, mt, out_channels), dtype=torch.float32, device=dev)
+    be.conv_umma(B=36, H=mt // 16, W=16, Cin=C, Cout=out_channels, taps=1, a_hi=v_hi, a_lo=v_lo, w_hi=u_hi, w_lo=u_lo,
+                 out=m, passes=3, weights_per_image=True, operand_f16=True)
+    out = torch.empty((B, H, W, out_channels), dtype=torch.float32, device=dev)
+    be.wino_output(m, B=B, H=H, W=W, Cout=out_channels, bias=bias, residual=residual,
+                   res_mode=cabi.RES_NONE if residual is None else cabi.RES_SAME, out=out)
+    return out
 
 
 def backend():
@@ -118,7 +157,8 @@ def _conv_backward(be, ctx_shape, a_hi, a_lo, weight, dy, need_dx, need_dw, need
     P = B * H * W
     dyn = _nhwc(dy)
     g_hi = g_lo = None
-    if need_dx:
+    wino_dx = need_dx and _wino_ok(be, B, H, W, Cout, Cin, k)
+    if need_dx and not wino_dx:
         g_hi = torch.empty((B, H, W, Cout), dtype=torch.bfloat16, device=dev)
         g_lo = torch.empty_like(g_hi)
     gt_hi = torch.empty((Cout, P), dtype=torch.bfloat16, device=dev)
@@ -129,7 +169,10 @@ def _conv_backward(be, ctx_shape, a_hi, a_lo, weight, dy, need_dx, need_dw, need
         ws_b = torch.empty(((P + 63) // 64) * Cout, dtype=torch.float32, device=dev)
     be.split_grad(dyn, g_hi, g_lo, gt_hi, gt_lo, dbias, ws_b)
     dxn = None
-    if need_dx:
+    if wino_dx:
+        # data gradient = conv of dY with the flipped, channel-swapped kernel -- on the Winograd path
+        dxn = _wino_conv(be, dyn.contiguous(), weight, dgrad=True, out_channels=Cin)
+    elif need_dx:
         # data gradient = the same conv with the kernel flipped and Cin/Cout swapped
         wd_hi, wd_lo = wd
         if wd_hi is None:
@@ -171,15 +214,24 @@ class GNActConv2dFn(torch.autograd.Function):
             fs, fh = scale.detach().contiguous().float(), shift.detach().contiguous().float()
         a_hi = torch.empty((B, H, W, Cin), dtype=torch.bfloat16, device=dev)
         a_lo = torch.empty_like(a_hi)
-        be.prep(xn, None, groups=32, mean=mean, rstd=rstd, gamma=gamma.detach(), beta=beta.detach(), film_scale=fs,
-                film_shift=fh, film_stride=0 if fs is None else fs.shape[1], silu=act, resample=resample,
-                act_hi=a_hi, act_lo=a_lo)
-        w_hi, w_lo, wd_hi, wd_lo = _pack_weights(be, weight, True)
-        out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=dev)
         rn = None if residual is None else _nhwc(residual.detach())       # + skip(x), fused in the epilogue
-        be.conv_umma(B=B, H=H, W=W, Cin=Cin, Cout=Cout, taps=k * k, a_hi=a_hi, a_lo=a_lo, w_hi=w_hi, w_lo=w_lo,
-                     bias=None if bias is None else bias.detach(), residual=rn,
-                     res_mode=cabi.RES_NONE if rn is None else cabi.RES_SAME, out=out, passes=3)
+        if resample == 0 and _wino_ok(be, B, H, W, Cin, Cout, k):
+            # Winograd forward; the input transform also writes the activated split planes the weight gradient needs
+            gn = dict(groups=32, mean=mean, rstd=rstd, gamma=gamma.detach(), beta=beta.detach(), film_scale=fs,
+                      film_shift=fh, film_stride=0 if fs is None else fs.shape[1], silu=act)
+            out = _wino_conv(be, xn.contiguous(), weight, dgrad=False, gn=gn, act_planes=(a_hi, a_lo),
+                             bias=None if bias is None else bias.detach(), residual=None if rn is None else rn.contiguous(),
+                             out_channels=Cout)
+            wd_hi = wd_lo = None              # the backward re-derives what it needs (Winograd dgrad planes)
+        else:
+            be.prep(xn, None, groups=32, mean=mean, rstd=rstd, gamma=gamma.detach(), beta=beta.detach(), film_scale=fs,
+                    film_shift=fh, film_stride=0 if fs is None else fs.shape[1], silu=act, resample=resample,
+                    act_hi=a_hi, act_lo=a_lo)
+            w_hi, w_lo, wd_hi, wd_lo = _pack_weights(be, weight, True)
+            out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=dev)
+            be.conv_umma(B=B, H=H, W=W, Cin=Cin, Cout=Cout, taps=k * k, a_hi=a_hi, a_lo=a_lo, w_hi=w_hi, w_lo=w_lo,
+                         bias=None if bias is None else bias.detach(), residual=rn,
+                         res_mode=cabi.RES_NONE if rn is None else cabi.RES_SAME, out=out, passes=3)
         ctx.save_for_backward(xn, mean, rstd, gamma, beta, fs, fh, a_hi, a_lo, weight, wd_hi, wd_lo)
         ctx.has_bias = bias is not None
         ctx.shape = (B, H, W, Cin, Cout, k)

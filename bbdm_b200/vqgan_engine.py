@@ -65,6 +65,12 @@ class VQGANEngine(KernelExecutor):
                 be.pack_weight_split(wt, ent["hi_pad"], ent["lo_pad"])
             ent["f32"] = be.empty((k * k, cin, cout), torch.float32, dev)
             be.pack_weight_f32(wt, ent["f32"])
+            if self.wino and "hi" in ent and k == 3 and min(cin, cout) >= self.wino_min_c \
+                    and (name.endswith(".conv1") or name.endswith(".conv2")):
+                # ResnetBlock 3x3 convs: Winograd-domain planes (csrc/winograd.cu), like the UNet's ResBlocks
+                ent["u_hi"] = be.empty((36, cout, cin), torch.float16, dev)
+                ent["u_lo"] = be.empty((36, cout, cin), torch.float16, dev)
+                be.wino_pack_weight(wt, ent["u_hi"], ent["u_lo"])
             w[name] = ent
 
         for name, m in self.vq.named_modules():
@@ -142,9 +148,33 @@ class VQGANEngine(KernelExecutor):
         umma1, umma2 = "hi" in e1 and W >= 4, "hi" in e2 and W >= 4
         fuse_skip = es is not None and es["k"] == 1 and umma2 and "hi" in es
         skip_umma = es is not None and not fuse_skip and "hi" in es and W >= 4
-        a_f32, a_hi, a_lo, r_hi, r_lo = self._gn_act(pool, x, m.norm1, umma1, want_raw_split=fuse_skip or skip_umma)
-        h1, _, _ = self._conv(pool, e1, a_f32=a_f32, a_hi=a_hi, a_lo=a_lo, shape=(B, H, W), stats=True)
-        pool.put(a_f32, a_hi, a_lo)
+        wino1, wino2 = umma1 and self._wino_ok(e1, B, H, W), umma2 and self._wino_ok(e2, B, H, W)
+        r_hi = r_lo = None
+        if wino1:
+            # Winograd conv1: the raw split planes a 1x1 shortcut needs come out of the same input pass
+            if fuse_skip or skip_umma:
+                r_hi, r_lo = pool.get(x.shape, torch.bfloat16), pool.get(x.shape, torch.bfloat16)
+            mean, rstd = self._stats(pool, x, None)
+            h1 = self._wino_conv(pool, e1, x, None, mean=mean, rstd=rstd, gamma=m.norm1.weight.detach(),
+                                 beta=m.norm1.bias.detach(), raw=None if r_hi is None else (r_hi, r_lo))
+            pool.put(mean, rstd)
+        else:
+            a_f32, a_hi, a_lo, r_hi, r_lo = self._gn_act(pool, x, m.norm1, umma1, want_raw_split=fuse_skip or skip_umma)
+            h1, _, _ = self._conv(pool, e1, a_f32=a_f32, a_hi=a_hi, a_lo=a_lo, shape=(B, H, W), stats=True)
+            pool.put(a_f32, a_hi, a_lo)
+        if wino2:
+            # Winograd conv2: the shortcut (1x1 GEMM or identity) enters as the output transform's residual
+            sk = None
+            if es is not None:
+                if "hi" in es and W >= 4 and r_hi is not None:
+                    sk, _, _ = self._conv(pool, es, a_hi=r_hi, a_lo=r_lo, shape=(B, H, W))
+                else:
+                    sk, _, _ = self._conv(pool, es, a_f32=x, shape=(B, H, W))
+            mean, rstd = self._stats(pool, h1, None)
+            out = self._wino_conv(pool, e2, h1, None, mean=mean, rstd=rstd, gamma=m.norm2.weight.detach(),
+                                  beta=m.norm2.bias.detach(), residual=x if sk is None else sk, res_mode=cabi.RES_SAME)
+            pool.put(mean, rstd, h1, r_hi, r_lo, sk)
+            return out
         b_f32, b_hi, b_lo, _, _ = self._gn_act(pool, h1, m.norm2, umma2)
         pool.put(h1)
         kw = dict(a_f32=b_f32, a_hi=b_hi, a_lo=b_lo, shape=(B, H, W), stats=True)
@@ -294,9 +324,24 @@ class VQGANEngine(KernelExecutor):
         return y, None
 
     # ------------------------------------------------------------------------------ public
+    # activation budget of one pass: 32 images of 256x256 (the cfg3 batch; ~25 GB of pooled NHWC tensors and operand
+    # planes).  Larger batches / resolutions run in chunks of this many image pixels -- the ends are 2-13 % of a
+    # sampled batch, so nothing is lost, and BASELINE configs[3] (64 x 512^2) would otherwise need > 180 GB.
+    max_pixels_per_pass = 32 * 256 * 256
+
+    def _chunks(self, n_images, image_pixels):
+        per = max(1, self.max_pixels_per_pass // max(1, image_pixels))
+        return [(i, min(n_images, i + per)) for i in range(0, n_images, per)]
+
     @torch.no_grad()
     def encode(self, x, quant_conv=True):
         """vqgan.encoder(x) [-> vqgan.quant_conv]   (LatentBrownianBridgeModel.py:73-82): NCHW in, NCHW out."""
+        ch = self._chunks(x.shape[0], x.shape[2] * x.shape[3])
+        if len(ch) == 1:
+            return self._encode_pass(x, quant_conv)
+        return torch.cat([self._encode_pass(x[a:b], quant_conv) for a, b in ch], 0)
+
+    def _encode_pass(self, x, quant_conv=True):
         self.refresh_weights()
         enc, w = self.vq.encoder, self._w
         pool = self._pool(x.device, ("enc",) + tuple(x.shape))
@@ -340,6 +385,16 @@ class VQGANEngine(KernelExecutor):
     @torch.no_grad()
     def decode(self, z, quant_conv_first=False, return_indices=False):
         """[quant_conv ->] quantize -> post_quant_conv -> decoder   (LatentBrownianBridgeModel.py:84-100)."""
+        f = 2 ** (self.vq.decoder.num_resolutions - 1)
+        ch = self._chunks(z.shape[0], z.shape[2] * z.shape[3] * f * f)
+        if len(ch) == 1:
+            return self._decode_pass(z, quant_conv_first, return_indices)
+        outs = [self._decode_pass(z[a:b], quant_conv_first, return_indices) for a, b in ch]
+        if return_indices:
+            return torch.cat([o[0] for o in outs], 0), torch.cat([o[1] for o in outs], 0)
+        return torch.cat(outs, 0)
+
+    def _decode_pass(self, z, quant_conv_first=False, return_indices=False):
         self.refresh_weights()
         dec, w = self.vq.decoder, self._w
         pool = self._pool(z.device, ("dec",) + tuple(z.shape))

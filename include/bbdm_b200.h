@@ -255,7 +255,9 @@ int bbdm_wino_geometry(int B, int H, int W, int* tiles_h, int* tiles_w, int64_t*
 /* cat(src1, src2) [B,H,W,C] fp32 -> act = silu?(GN_affine(x) * (1+film_scale) + film_shift) (as bbdm_prep_operand)
  * -> V = B^T act B for every 6x6 tile (stride 4, origin (-1,-1), zero padding of the ACTIVATED tensor) ->
  * split-fp16 planes v_hi, v_lo [36][tiles_total][C].  raw_hi/raw_lo (optional): split-bf16 NHWC planes of the
- * raw input (A operand of the ResBlock's 1x1 skip convolution, openaimodel.py:244). */
+ * raw input (A operand of the ResBlock's 1x1 skip convolution, openaimodel.py:244).
+ * mean == NULL (silu must be 0): identity -- the tensor is transformed as it is (the data-gradient convolution of
+ * the training path transforms dY). */
 typedef struct {
   const float* src1; int c1;
   const float* src2; int c2;
@@ -266,6 +268,8 @@ typedef struct {
   int silu;
   void* v_hi; void* v_lo;
   void* raw_hi; void* raw_lo;
+  void* act_hi; void* act_lo;   /* optional: split-bf16 NHWC planes of the ACTIVATED tensor (training: operand of the
+                                   weight-gradient GEMM, bbdm_conv_wgrad) */
 } BbdmWinoInputArgs;
 int bbdm_wino_input(const BbdmWinoInputArgs* a, void* stream);
 
@@ -282,8 +286,10 @@ typedef struct {
 } BbdmWinoOutputArgs;
 int bbdm_wino_output(const BbdmWinoOutputArgs* a, void* stream);
 
-/* w [Cout,Cin,3,3] fp32 -> U = 2^8 * G w G^T (fp64 arithmetic), split-fp16 planes u_hi, u_lo [36][Cout][Cin]. */
-int bbdm_wino_pack_weight(const float* w, int Cout, int Cin, void* u_hi, void* u_lo, void* stream);
+/* w [Cout,Cin,3,3] fp32 -> U = 2^8 * G w G^T (fp64 arithmetic), split-fp16 planes u_hi, u_lo [36][Cout][Cin].
+ * dgrad != 0: the planes of the data-gradient convolution instead ([36][Cin][Cout], kernel flipped, channels
+ * swapped; cf. bbdm_pack_weight_split_dgrad). */
+int bbdm_wino_pack_weight(const float* w, int Cout, int Cin, int dgrad, void* u_hi, void* u_lo, void* stream);
 
 /* General fp32 direct convolution on CUDA cores (any Cin/Cout, k in {1,3}, stride 1 or 2,
  * pad k/2): stem (openaimodel.py:524), head (:690), conv-mode Downsample/Upsample (:109,150)

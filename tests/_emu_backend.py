@@ -221,21 +221,30 @@ class EmuBackend:
         hi.copy_(h)
         lo.copy_((x.float() - h.float()).to(torch.float16))
 
-    def wino_input(self, src1, src2, *, groups, mean, rstd, gamma, beta, film_scale=None, film_shift=None,
-                   film_stride=0, silu=True, v_hi, v_lo, raw_hi=None, raw_lo=None):
+    def wino_input(self, src1, src2, *, groups=32, mean=None, rstd=None, gamma=None, beta=None, film_scale=None,
+                   film_shift=None, film_stride=0, silu=True, v_hi, v_lo, raw_hi=None, raw_lo=None, act_hi=None,
+                   act_lo=None):
         self.calls.append("wino_input")
         x = src1 if src2 is None else torch.cat([src1, src2], dim=3)
         assert not torch.isnan(x).any()
         B, H, W, C = x.shape
-        a = O.op_gn_act(x, mean, rstd, gamma, beta, film_scale, film_shift, silu, 0)        # [B,H,W,C]
+        if mean is None:
+            assert not silu and film_scale is None
+            a = x.float()
+        else:
+            a = O.op_gn_act(x, mean, rstd, gamma, beta, film_scale, film_shift, silu, 0)    # [B,H,W,C]
+        if act_hi is not None:
+            self._write_split(a, act_hi, act_lo)
         t = F.pad(a.permute(0, 3, 1, 2).double(), (1, 1, 1, 1)).unfold(2, 6, 4).unfold(3, 6, 4)   # [B,C,th,tw,6,6]
         V = torch.einsum("ij,bcxyjk,lk->ilbxyc", self._BT, t, self._BT)                      # [6,6,B,th,tw,C]
         self._write_split_f16(V.reshape(v_hi.shape), v_hi, v_lo)
         if raw_hi is not None:
             self._write_split(x, raw_hi, raw_lo)
 
-    def wino_pack_weight(self, w, u_hi, u_lo):
+    def wino_pack_weight(self, w, u_hi, u_lo, dgrad=False):
         self.calls.append("wino_pack_weight")
+        if dgrad:
+            w = w.flip(2, 3).transpose(0, 1)
         U = torch.einsum("ij,kcjl,ml->imkc", self._G, w.double(), self._G) * 256.0           # [6,6,Cout,Cin]
         self._write_split_f16(U.reshape(u_hi.shape), u_hi, u_lo)
 

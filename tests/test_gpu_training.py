@@ -126,9 +126,12 @@ def test_training_step_native_convs_match_library_graph():
     assert worst < 2e-3
 
 
-@pytest.mark.parametrize("B,H,W,C,Cout,film", [(2, 16, 16, 64, 128, True), (3, 8, 8, 128, 64, False), (2, 32, 32, 640, 128, True)])
+@pytest.mark.parametrize("B,H,W,C,Cout,film", [(2, 16, 16, 64, 128, True), (3, 8, 8, 128, 64, False), (2, 32, 32, 640, 128, True),
+                                                (8, 32, 32, 256, 256, True),     # Winograd forward + data gradient (512 tiles)
+                                                (2, 64, 64, 256, 512, False)])   # Winograd: 256 tiles per image
 def test_gn_act_conv_function_gradients(B, H, W, C, Cout, film):
     """conv(silu(GN(x)*(1+scale)+shift)) fused Function: outputs and ALL gradients vs an fp64 torch graph."""
+    from bbdm_b200 import cabi, train
     from bbdm_b200.train import GNActConv2dFn
     mk = lambda t: t.to(DEV).requires_grad_(True)
     x = mk(rnd((B, C, H, W), 10) + 0.2)
@@ -138,8 +141,10 @@ def test_gn_act_conv_function_gradients(B, H, W, C, Cout, film):
     w, b = mk(rnd((Cout, C, 3, 3), 15, 0.05)), mk(rnd((Cout,), 16, 0.1))
     gy = rnd((B, Cout, H, W), 17, 0.2).to(DEV)
     res = mk(rnd((B, Cout, H, W), 18)) if film else None            # fused "+ skip" operand
+    assert train._wino_ok(train.backend(), B, H, W, C, Cout, 3) == (min(C, Cout) >= 256)
     y = GNActConv2dFn.apply(x, gamma, beta, scale, shift, w, b, 0, res)
     y.backward(gy)
+    train.backend().check_fault()
 
     d = lambda t: None if t is None else t.detach().double().cpu().requires_grad_(True)
     xd, gd, bd, sd, hd, wd, bbd, rd = d(x), d(gamma), d(beta), d(scale), d(shift), d(w), d(b), d(res)

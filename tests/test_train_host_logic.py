@@ -48,6 +48,42 @@ def test_conv2d_function(emu, k, bias):
     assert {"pack_weight_split_both", "conv_umma", "split_grad", "conv_wgrad"} <= set(emu.calls)
 
 
+@pytest.mark.parametrize("film", [True, False])
+def test_gn_act_conv_function_winograd_route(emu, film, monkeypatch):
+    """Forward and data gradient on the Winograd path (input transform that also emits the activated split planes for
+    the weight gradient, 36 position GEMMs, output transform with bias + residual; dY transformed in identity mode with
+    the flipped / channel-swapped kernel), forced on for a 64-channel 32x32 case (128 tiles)."""
+    from bbdm_b200 import train
+    from bbdm_b200.train import GNActConv2dFn
+    monkeypatch.setattr(train, "WINO_MIN_C", 64)
+    monkeypatch.setattr(train, "WINO_MIN_TILES", 128)
+    B, C, H, W, Cout = 2, 64, 32, 32, 128
+    x = (rnd((B, C, H, W), 10) + 0.2).requires_grad_(True)
+    gamma, beta = (1 + 0.1 * rnd((C,), 11)).requires_grad_(True), (0.1 * rnd((C,), 12)).requires_grad_(True)
+    scale = (0.3 * rnd((B, C), 13)).requires_grad_(True) if film else None
+    shift = (0.3 * rnd((B, C), 14)).requires_grad_(True) if film else None
+    w, b = rnd((Cout, C, 3, 3), 15, 0.05).requires_grad_(True), rnd((Cout,), 16, 0.1).requires_grad_(True)
+    res = rnd((B, Cout, H, W), 18).requires_grad_(True) if film else None
+    gy = rnd((B, Cout, H, W), 17, 0.2)
+    y = GNActConv2dFn.apply(x, gamma, beta, scale, shift, w, b, 0, res, True)
+    y.backward(gy)
+    assert emu.calls.count("wino_input") == 2 and emu.calls.count("wino_output") == 2 and "conv_wgrad" in emu.calls
+    xd, gd, bd, sd, hd, wd, bbd, rd = (d64(t) for t in (x, gamma, beta, scale, shift, w, b, res))
+    h = F.group_norm(xd, 32, gd, bd, 1e-5)
+    if film:
+        h = h * (1 + sd[:, :, None, None]) + hd[:, :, None, None]
+    yd = F.conv2d(F.silu(h), wd, bbd, padding=1)
+    if res is not None:
+        yd = yd + rd
+    yd.backward(gy.double())
+    assert rel_dev(y, yd) < 3e-5
+    for name, a, r in [("x", x, xd), ("gamma", gamma, gd), ("beta", beta, bd), ("w", w, wd), ("b", b, bbd)]:
+        assert rel_dev(a.grad, r.grad) < 1e-4, name
+    if film:
+        assert rel_dev(scale.grad, sd.grad) < 1e-4 and rel_dev(shift.grad, hd.grad) < 1e-4
+        assert rel_dev(res.grad, rd.grad) < 1e-6
+
+
 @pytest.mark.parametrize("film,resample,act", [(True, 0, True), (False, 1, True), (False, 2, True), (False, 0, False)])
 def test_gn_act_conv_function(emu, film, resample, act):
     from bbdm_b200.train import GNActConv2dFn

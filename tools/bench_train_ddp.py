@@ -76,6 +76,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--library", action="store_true", help="stock PyTorch TF32 graph instead of the native kernels")
+    ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam instead of bbdm_b200.optim.FusedAdam")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -92,7 +93,11 @@ def main():
     B = cfg["batch"]
     x = bench.synth((B, 3, 256, 256), 100 + rank).to(dev)            # different data per rank, same seed for t/noise (Q6)
     xc = bench.synth((B, 3, 256, 256), 200 + rank).to(dev)
-    opt = torch.optim.Adam(net.get_parameters(), lr=1e-4, betas=(0.9, 0.999))
+    if a.library or a.torch_adam:
+        opt = torch.optim.Adam(net.get_parameters(), lr=1e-4, betas=(0.9, 0.999))
+    else:
+        from bbdm_b200.optim import FusedAdam                       # one multi-tensor launch per step
+        opt = FusedAdam(net.get_parameters(), lr=1e-4, betas=(0.9, 0.999))
     model = net
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], output_device=local)
@@ -132,7 +137,7 @@ def main():
     ms, loss = timed(a.steps)
     row = {"what": "LBBDM-f4 training micro-step: 2 VQGAN encodes (no grad) + q_sample + UNet fwd/bwd + DDP gradient allreduce + Adam",
            "impl": "stock PyTorch TF32 (library)" if a.library else "bbdm_b200 native kernels (split-bf16 x3)",
-           "n_gpus": world, "batch_per_gpu": B, "ms_per_micro_step": ms, "micro_steps_per_s": 1e3 / ms,
+           "optimizer": type(opt).__name__, "n_gpus": world, "batch_per_gpu": B, "ms_per_micro_step": ms, "micro_steps_per_s": 1e3 / ms,
            "samples_per_s": world * B * 1e3 / ms, "loss": loss, "steps": a.steps, "warmup": a.warmup,
            "grad_bytes_allreduced": sum(p.numel() for p in net.get_parameters()) * 4,
            "max_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
