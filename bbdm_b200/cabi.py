@@ -33,6 +33,7 @@ SYMBOLS = [
     "bbdm_conv_wgrad_direct", "bbdm_attention_bwd", "bbdm_conv_direct_pad", "bbdm_softmax_rows_split", "bbdm_vq_nearest", "bbdm_s2d_split", "bbdm_pack_weight_split_both",
     "bbdm_wino_geometry", "bbdm_wino_input", "bbdm_wino_output", "bbdm_wino_pack_weight",
     "bbdm_optim_chunk_elems", "bbdm_adam_multi", "bbdm_ema_multi", "bbdm_denorm_to_uint8",
+    "bbdm_layernorm_split", "bbdm_geglu_split", "bbdm_attention_cross",
 ]
 
 
@@ -142,6 +143,9 @@ def load():
     lib.bbdm_wino_output.argtypes = [C.POINTER(WinoOutputArgs), vp]
     lib.bbdm_wino_pack_weight.argtypes = [vp, i, i, i, vp, vp, vp]
     lib.bbdm_denorm_to_uint8.argtypes = [vp, i, i, i, i, i, vp, vp]
+    lib.bbdm_layernorm_split.argtypes = [vp, i64, i, vp, vp, f, vp, vp, vp, vp]
+    lib.bbdm_geglu_split.argtypes = [vp, i64, i, vp, vp, vp, vp]
+    lib.bbdm_attention_cross.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp, vp]
     lib.bbdm_optim_chunk_elems.argtypes = []
     lib.bbdm_adam_multi.argtypes = [vp, vp, vp, vp, vp, vp, i, vp, vp, f, f, f, f, f, i64, vp, C.c_double, vp]
     lib.bbdm_ema_multi.argtypes = [vp, vp, vp, vp, vp, i, vp, C.c_double, i, vp]
@@ -379,6 +383,27 @@ class CudaBackend:
         Cout, Cin = w.shape[0], w.shape[1]
         check(self.lib.bbdm_wino_pack_weight(ptr(_req(w)), Cout, Cin, int(dgrad), ptr(_req(u_hi, torch.float16)),
                                              ptr(_req(u_lo, torch.float16)), stream()))
+        LAUNCHES["n"] += 1
+
+    # -- SpatialTransformer pieces --------------------------------------------------------------------------
+    def layernorm_split(self, x, gamma, beta, eps, out_f32=None, out_hi=None, out_lo=None):
+        Cc = x.shape[-1]
+        check(self.lib.bbdm_layernorm_split(ptr(_req(x)), x.numel() // Cc, Cc, ptr(_req(gamma)), ptr(_req(beta)), eps,
+                                            ptr(out_f32), ptr(out_hi), ptr(out_lo), stream()))
+        LAUNCHES["n"] += 1
+
+    def geglu_split(self, u, out_f32=None, out_hi=None, out_lo=None):
+        N2 = u.shape[-1]
+        check(self.lib.bbdm_geglu_split(ptr(_req(u)), u.numel() // N2, N2 // 2, ptr(out_f32), ptr(out_hi), ptr(out_lo),
+                                        stream()))
+        LAUNCHES["n"] += 1
+
+    def attention_cross(self, q_hi, q_lo, kv_hi, kv_lo, heads, out_f32=None, out_hi=None, out_lo=None):
+        B, Tq, Cc = q_hi.shape
+        Tkv = kv_hi.shape[1]
+        check(self.lib.bbdm_attention_cross(ptr(_req(q_hi, torch.bfloat16)), ptr(_req(q_lo, torch.bfloat16)),
+                                            ptr(_req(kv_hi, torch.bfloat16)), ptr(_req(kv_lo, torch.bfloat16)), B, Tq, Tkv,
+                                            Cc, heads, ptr(out_f32), ptr(out_hi), ptr(out_lo), stream()))
         LAUNCHES["n"] += 1
 
     # -- sample_to_eval output path ------------------------------------------------------------------------

@@ -41,10 +41,19 @@ __device__ __forceinline__ float ex2f(float x) {
 }
 __device__ __forceinline__ void split2p(float x, float y, uint32_t& hi, uint32_t& lo) { split2x(x, y, hi, lo); }
 
+// Operand addressing: queries come from (q_hi, q_lo) [B][Tq][rs_q] at column qoff0 + head*hstride, keys / values from
+// (kv_hi, kv_lo) [B][T][rs_kv] at koff0 / voff0 + head*hstride.  Self-attention passes the same planes for both
+// (T == Tq); cross-attention (SpatialTransformer.attn2, reference attention.py:152-192) a separate K|V tensor with
+// its own length T.
+struct AttnOperands {
+  const __nv_bfloat16* q_hi; const __nv_bfloat16* q_lo; int64_t rs_q; int qoff0;
+  const __nv_bfloat16* kv_hi; const __nv_bfloat16* kv_lo; int64_t rs_kv; int koff0, voff0;
+  int hstride, Tq;
+};
+
 template <int D>
 __global__ void __launch_bounds__(256)
-attention_split_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bfloat16* __restrict__ qkv_lo,
-                       int T, int C, int heads, int order, float scale_log2,
+attention_split_kernel(const AttnOperands ops, int T, int C, int heads, float scale_log2,
                        float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
                        __nv_bfloat16* __restrict__ out_lo) {
   constexpr int KT = 64;                  // keys per tile
@@ -57,12 +66,14 @@ attention_split_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bflo
   const int b = bh / heads, head = bh % heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int64_t rs = 3 * (int64_t)C;      // row stride (elements)
-  int qoff, koff, voff;
-  if (order == 0) { qoff = head * 3 * D; koff = qoff + D; voff = qoff + 2 * D; }
-  else { qoff = head * D; koff = C + head * D; voff = 2 * C + head * D; }
-  const __nv_bfloat16* base_hi = qkv_hi + (int64_t)b * T * rs;
-  const __nv_bfloat16* base_lo = qkv_lo + (int64_t)b * T * rs;
+  const int64_t rs = ops.rs_kv, rs_q = ops.rs_q;      // row strides (elements)
+  const int Tq = ops.Tq;
+  const int qoff = ops.qoff0 + head * ops.hstride, koff = ops.koff0 + head * ops.hstride,
+            voff = ops.voff0 + head * ops.hstride;
+  const __nv_bfloat16* base_hi = ops.kv_hi + (int64_t)b * T * rs;
+  const __nv_bfloat16* base_lo = ops.kv_lo + (int64_t)b * T * rs;
+  const __nv_bfloat16* qbase_hi = ops.q_hi + (int64_t)b * Tq * rs_q;
+  const __nv_bfloat16* qbase_lo = ops.q_lo + (int64_t)b * Tq * rs_q;
 
   // ---- stage loader: 4 plane tiles x KT rows x (D/8) 16-byte chunks -------------------------
   auto load_tile = [&](int stage, int k0) {
@@ -91,10 +102,10 @@ attention_split_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bflo
       for (int r2 = 0; r2 < 2; ++r2) {
         const int qr = q0 + g + r2 * 8;
         uint32_t vh = 0, vl = 0;
-        if (qr < T) {
-          const int64_t o = qr * rs + qoff + ks * 16 + h2 * 8 + 2 * t;
-          vh = *reinterpret_cast<const uint32_t*>(base_hi + o);
-          vl = *reinterpret_cast<const uint32_t*>(base_lo + o);
+        if (qr < Tq) {
+          const int64_t o = qr * rs_q + qoff + ks * 16 + h2 * 8 + 2 * t;
+          vh = *reinterpret_cast<const uint32_t*>(qbase_hi + o);
+          vl = *reinterpret_cast<const uint32_t*>(qbase_lo + o);
         }
         qh[ks][h2 * 2 + r2] = vh;
         ql[ks][h2 * 2 + r2] = vl;
@@ -214,9 +225,9 @@ attention_split_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bflo
 #pragma unroll
   for (int r2 = 0; r2 < 2; ++r2) {
     const int qr = q0 + g + r2 * 8;
-    if (qr >= T) continue;
+    if (qr >= Tq) continue;
     const float inv = 1.0f / l_run[r2];
-    const int64_t off = ((int64_t)b * T + qr) * C + head * D + 2 * t;
+    const int64_t off = ((int64_t)b * Tq + qr) * C + head * D + 2 * t;
 #pragma unroll
     for (int jd = 0; jd < D / 8; ++jd) {
       const float x = o[jd][2 * r2] * inv, y = o[jd][2 * r2 + 1] * inv;
@@ -235,31 +246,25 @@ attention_split_kernel(const __nv_bfloat16* __restrict__ qkv_hi, const __nv_bflo
 
 using namespace bbdm;
 
-extern "C" int bbdm_attention_split(const void* qkv_hi, const void* qkv_lo, int B, int T, int C, int heads,
-                                    int order, float* out_f32, void* out_hi, void* out_lo, void* stream) {
-  BBDM_REQUIRE(qkv_hi && qkv_lo && (out_f32 || (out_hi && out_lo)), "attention_split: null pointer");
-  BBDM_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "attention_split: hi/lo must come in pairs");
-  BBDM_REQUIRE(B > 0 && T > 0 && heads > 0 && C % heads == 0, "attention_split: bad shape");
-  BBDM_REQUIRE(order == 0 || order == 1, "attention_split: order must be 0 (legacy) or 1");
+static int launch_attention_split(const AttnOperands& ops, int B, int T, int C, int heads, float* out_f32, void* out_hi,
+                                  void* out_lo, void* stream) {
   const int D = C / heads;
   BBDM_REQUIRE((int64_t)B * heads <= 65535, "attention_split: B*heads too large");
-  dim3 grid((T + 127) / 128, B * heads);
+  dim3 grid((ops.Tq + 127) / 128, B * heads);
   cudaStream_t s = (cudaStream_t)stream;
   // softmax((q s)(k s)) with s = D^-1/4  ==  2^(log2(e) * D^-1/2 * (q.k) - max)
   const float scale_log2 = (float)(1.4426950408889634 / sqrt((double)D));
-  const __nv_bfloat16* qh = (const __nv_bfloat16*)qkv_hi;
-  const __nv_bfloat16* ql = (const __nv_bfloat16*)qkv_lo;
   __nv_bfloat16* oh = (__nv_bfloat16*)out_hi;
   __nv_bfloat16* ol = (__nv_bfloat16*)out_lo;
 #define BBDM_AL(DD)                                                                                       \
   {                                                                                                       \
     const size_t smem = (size_t)2 * 4 * 64 * (DD + 8) * 2;                                                \
-    static DeviceOnce cfgd;                                                                                \
-    if (cfgd.need()) {                                                                                          \
+    static DeviceOnce cfgd;                                                                               \
+    if (cfgd.need()) {                                                                                    \
       BBDM_CUDA_CHECK(cudaFuncSetAttribute(attention_split_kernel<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      cfgd.mark();                                                                                         \
+      cfgd.mark();                                                                                        \
     }                                                                                                     \
-    attention_split_kernel<DD><<<grid, 256, smem, s>>>(qh, ql, T, C, heads, order, scale_log2, out_f32, oh, ol); \
+    attention_split_kernel<DD><<<grid, 256, smem, s>>>(ops, T, C, heads, scale_log2, out_f32, oh, ol);   \
   }
   if (D == 64) BBDM_AL(64)
   else if (D == 32) BBDM_AL(32)
@@ -271,4 +276,36 @@ extern "C" int bbdm_attention_split(const void* qkv_hi, const void* qkv_lo, int 
 #undef BBDM_AL
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
+}
+
+extern "C" int bbdm_attention_split(const void* qkv_hi, const void* qkv_lo, int B, int T, int C, int heads,
+                                    int order, float* out_f32, void* out_hi, void* out_lo, void* stream) {
+  BBDM_REQUIRE(qkv_hi && qkv_lo && (out_f32 || (out_hi && out_lo)), "attention_split: null pointer");
+  BBDM_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "attention_split: hi/lo must come in pairs");
+  BBDM_REQUIRE(B > 0 && T > 0 && heads > 0 && C % heads == 0, "attention_split: bad shape");
+  BBDM_REQUIRE(order == 0 || order == 1, "attention_split: order must be 0 (legacy) or 1");
+  const int D = C / heads;
+  AttnOperands ops;
+  ops.q_hi = ops.kv_hi = (const __nv_bfloat16*)qkv_hi;
+  ops.q_lo = ops.kv_lo = (const __nv_bfloat16*)qkv_lo;
+  ops.rs_q = ops.rs_kv = 3 * (int64_t)C;
+  ops.Tq = T;
+  if (order == 0) { ops.hstride = 3 * D; ops.qoff0 = 0; ops.koff0 = D; ops.voff0 = 2 * D; }
+  else { ops.hstride = D; ops.qoff0 = 0; ops.koff0 = C; ops.voff0 = 2 * C; }
+  return launch_attention_split(ops, B, T, C, heads, out_f32, out_hi, out_lo, stream);
+}
+
+extern "C" int bbdm_attention_cross(const void* q_hi, const void* q_lo, const void* kv_hi, const void* kv_lo, int B,
+                                    int Tq, int Tkv, int C, int heads, float* out_f32, void* out_hi, void* out_lo,
+                                    void* stream) {
+  BBDM_REQUIRE(q_hi && q_lo && kv_hi && kv_lo && (out_f32 || (out_hi && out_lo)), "attention_cross: null pointer");
+  BBDM_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "attention_cross: hi/lo must come in pairs");
+  BBDM_REQUIRE(B > 0 && Tq > 0 && Tkv > 0 && heads > 0 && C % heads == 0, "attention_cross: bad shape");
+  AttnOperands ops;
+  ops.q_hi = (const __nv_bfloat16*)q_hi; ops.q_lo = (const __nv_bfloat16*)q_lo;
+  ops.kv_hi = (const __nv_bfloat16*)kv_hi; ops.kv_lo = (const __nv_bfloat16*)kv_lo;
+  ops.rs_q = C; ops.rs_kv = 2 * (int64_t)C;
+  ops.Tq = Tq;
+  ops.hstride = C / heads; ops.qoff0 = 0; ops.koff0 = 0; ops.voff0 = C;
+  return launch_attention_split(ops, B, Tkv, C, heads, out_f32, out_hi, out_lo, stream);
 }

@@ -19,6 +19,7 @@ import torch.nn as nn
 
 from . import cabi
 from .weights import upsample_phase_weights
+from .transformer import SpatialTransformer
 from .unet import (AttentionBlock, Downsample, ResBlock, TimestepEmbedSequential, UNetModel,
                    Upsample, timestep_embedding)
 
@@ -108,7 +109,8 @@ class KernelExecutor:
     def pool_bytes(self):
         return sum(p.bytes for p in self._pools.values())
 
-    def _stats(self, pool, src1, src2):
+    def _stats(self, pool, src1, src2, eps=None):
+        eps = self.gn_eps if eps is None else eps
         B = src1.shape[0]
         mean, rstd = pool.get((B, GN_GROUPS)), pool.get((B, GN_GROUPS))
         g1 = getattr(src1, "_gn", None)
@@ -116,12 +118,12 @@ class KernelExecutor:
         if g1 is not None and (src2 is None or g2 is not None):
             # both tensors came out of the tensor-core conv: its epilogue already reduced them
             self.be.gn_finalize_partials(g1[0], g1[1], None if g2 is None else g2[0], 0 if g2 is None else g2[1],
-                                         B, src1.shape[1] * src1.shape[2], GN_GROUPS, self.gn_eps, mean, rstd)
+                                         B, src1.shape[1] * src1.shape[2], GN_GROUPS, eps, mean, rstd)
             return mean, rstd
         if self._gn_ws is None or self._gn_ws.numel() < B * GN_GROUPS * cabi.GN_MAX_SLICES * 2 \
                 or self._gn_ws.device != src1.device:
             self._gn_ws = self.be.empty((B * GN_GROUPS * cabi.GN_MAX_SLICES * 2,), torch.float64, src1.device)
-        self.be.gn_stats(src1, src2, GN_GROUPS, self.gn_eps, mean, rstd, self._gn_ws)
+        self.be.gn_stats(src1, src2, GN_GROUPS, eps, mean, rstd, self._gn_ws)
         return mean, rstd
 
     def _conv(self, pool, ent, *, a_f32=None, a_hi=None, a_lo=None, shape, bias=None, residual=None,
@@ -252,12 +254,15 @@ class UNetEngine(KernelExecutor):
             return be.empty(tuple(shape), dtype, dev)
 
         def pack(conv, name):
-            wt = conv.weight.detach()
-            if wt.dim() == 3:                       # Conv1d [Cout, Cin, 1]
+            pack_tensor(conv.weight, conv.bias, name)
+
+        def pack_tensor(weight, bias, name):
+            wt = weight.detach()
+            while wt.dim() < 4:                     # Conv1d [Cout, Cin, 1], Linear [out, in]
                 wt = wt.unsqueeze(-1)
             wt = wt.contiguous()
             cout, cin, k = wt.shape[0], wt.shape[1], wt.shape[2]
-            ent = {"cout": cout, "cin": cin, "k": k, "bias": conv.bias.detach() if conv.bias is not None else None}
+            ent = {"cout": cout, "cin": cin, "k": k, "bias": bias.detach() if bias is not None else None}
             if cin % 64 == 0 and cout % 64 == 0 and k in (1, 3):
                 hi = buf(name, "hi", (k * k, cout, cin), torch.bfloat16)
                 lo = buf(name, "lo", (k * k, cout, cin), torch.bfloat16)
@@ -272,8 +277,8 @@ class UNetEngine(KernelExecutor):
                 if made:
                     hi.zero_(); lo.zero_()
                 bp.zero_()
-                if conv.bias is not None:
-                    bp[:cout].copy_(conv.bias.detach())
+                if bias is not None:
+                    bp[:cout].copy_(bias.detach())
                 be.pack_weight_split(wt, hi, lo)
                 ent["hi_pad"], ent["lo_pad"], ent["bias_pad"] = hi, lo, bp
             f32 = buf(name, "f32", (k * k, cin, cout), torch.float32)
@@ -298,6 +303,20 @@ class UNetEngine(KernelExecutor):
                 film_b.append(b)
                 w[name + "#film"] = (off, n)
                 off += n
+        for name, m in u.named_modules():
+            if isinstance(m, SpatialTransformer):
+                # every nn.Linear of the transformer blocks as a 1x1 "conv" over the token grid; q|k|v of the
+                # self-attention (and k|v of the cross-attention) concatenated into one GEMM each
+                for j, blk in enumerate(m.transformer_blocks):
+                    pre = f"{name}.transformer_blocks.{j}"
+                    a1, a2 = blk.attn1, blk.attn2
+                    pack_tensor(torch.cat([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], 0), None, pre + ".attn1.qkv")
+                    pack_tensor(a1.to_out[0].weight, a1.to_out[0].bias, pre + ".attn1.to_out.0")
+                    pack_tensor(a2.to_q.weight, None, pre + ".attn2.to_q")
+                    pack_tensor(torch.cat([a2.to_k.weight, a2.to_v.weight], 0), None, pre + ".attn2.to_kv")
+                    pack_tensor(a2.to_out[0].weight, a2.to_out[0].bias, pre + ".attn2.to_out.0")
+                    pack_tensor(blk.ff.net[0].proj.weight, blk.ff.net[0].proj.bias, pre + ".ff.net.0.proj")
+                    pack_tensor(blk.ff.net[2].weight, blk.ff.net[2].bias, pre + ".ff.net.2")
         if self.wino:
             # stride-1 3x3 ResBlock convs: Winograd-domain weight planes U = 2^8 G g G^T, fp16 hi/lo [36][Cout][Cin]
             for name, m in u.named_modules():
@@ -530,6 +549,92 @@ class UNetEngine(KernelExecutor):
         pool.put(o_f32, o_hi, o_lo)
         return out
 
+    def _spatial_transformer(self, pool, name, m: SpatialTransformer, x, ctx):
+        """GroupNorm(1e-6) -> proj_in -> [LN -> self-attention -> +, LN -> cross-attention(context) -> +,
+        LN -> GEGLU feed-forward -> +] x depth -> proj_out -> + x   (reference attention.py:196-264).  Every Linear /
+        1x1 conv is a tcgen05 GEMM over the token grid whose epilogue adds the residual; LayerNorm and GEGLU write the
+        next GEMM's split operand planes directly."""
+        be, w = self.be, self._w
+        B, H, W, Cc = x.shape
+        T, heads, d = H * W, m.n_heads, m.d_head
+        inner = heads * d
+        if d not in (16, 32, 64):
+            raise NotImplementedError(f"SpatialTransformer head_dim {d}: the sm_100a attention kernels take 16/32/64")
+        if not (self._umma_ok(Cc, inner, W) and inner % 64 == 0):
+            raise NotImplementedError("SpatialTransformer: channel counts must be multiples of 64 (tensor-core GEMMs)")
+        bf = torch.bfloat16
+        tok = (B, H, W, inner)
+        mean, rstd = self._stats(pool, x, None, eps=m.norm.eps)
+        a_hi, a_lo = pool.get(x.shape, bf), pool.get(x.shape, bf)
+        be.prep(x, None, groups=GN_GROUPS, mean=mean, rstd=rstd, gamma=m.norm.weight.detach(), beta=m.norm.bias.detach(),
+                silu=False, resample=cabi.RESAMPLE_NONE, act_hi=a_hi, act_lo=a_lo)
+        pool.put(mean, rstd)
+        h, _, _ = self._conv(pool, w[name + ".proj_in"], a_hi=a_hi, a_lo=a_lo, shape=(B, H, W))
+        pool.put(a_hi, a_lo)
+
+        def layernorm(ln, src):
+            n_hi, n_lo = pool.get(tok, bf), pool.get(tok, bf)
+            be.layernorm_split(src, ln.weight.detach(), ln.bias.detach(), ln.eps, out_hi=n_hi, out_lo=n_lo)
+            return n_hi, n_lo
+
+        def project_out(ent, o_hi, o_lo, res):
+            new, _, _ = self._conv(pool, ent, a_hi=o_hi, a_lo=o_lo, shape=(B, H, W), residual=res, res_mode=cabi.RES_SAME)
+            pool.put(o_hi, o_lo, res)
+            return new
+
+        for j, blk in enumerate(m.transformer_blocks):
+            pre = f"{name}.transformer_blocks.{j}"
+            # ---- self-attention ----------------------------------------------------------------------------------
+            n_hi, n_lo = layernorm(blk.norm1, h)
+            _, q_hi, q_lo = self._conv(pool, w[pre + ".attn1.qkv"], a_hi=n_hi, a_lo=n_lo, shape=(B, H, W), out_split=True,
+                                       want_f32=False)
+            pool.put(n_hi, n_lo)
+            o_hi, o_lo = pool.get(tok, bf), pool.get(tok, bf)
+            attn = be.attention_tc if (d == 64 and self.attention_impl == "tcgen05") else be.attention_split
+            attn(q_hi.view(B, T, 3 * inner), q_lo.view(B, T, 3 * inner), heads, 1, None, o_hi.view(B, T, inner),
+                 o_lo.view(B, T, inner))
+            pool.put(q_hi, q_lo)
+            h = project_out(w[pre + ".attn1.to_out.0"], o_hi, o_lo, h)
+            # ---- cross-attention over the conditioning tokens (or over h itself without a context) ------------------
+            n_hi, n_lo = layernorm(blk.norm2, h)
+            _, q_hi, q_lo = self._conv(pool, w[pre + ".attn2.to_q"], a_hi=n_hi, a_lo=n_lo, shape=(B, H, W), out_split=True,
+                                       want_f32=False)
+            ekv = w[pre + ".attn2.to_kv"]
+            if ctx is None:
+                _, kv_hi, kv_lo = self._conv(pool, ekv, a_hi=n_hi, a_lo=n_lo, shape=(B, H, W), out_split=True, want_f32=False)
+                Tc = T
+            else:
+                Bc, Hc, Wc, _ = ctx.shape
+                Tc = Hc * Wc
+                kv, _, _ = self._conv(pool, ekv, a_f32=ctx, shape=(Bc, Hc, Wc))          # few context channels: fp32 direct
+                kv_hi, kv_lo = pool.get(kv.shape, bf), pool.get(kv.shape, bf)
+                be.prep(kv, None, resample=cabi.RESAMPLE_NONE, raw_hi=kv_hi, raw_lo=kv_lo)
+                pool.put(kv)
+            pool.put(n_hi, n_lo)
+            o_hi, o_lo = pool.get(tok, bf), pool.get(tok, bf)
+            be.attention_cross(q_hi.view(B, T, inner), q_lo.view(B, T, inner), kv_hi.view(B, Tc, 2 * inner),
+                               kv_lo.view(B, Tc, 2 * inner), heads, None, o_hi.view(B, T, inner), o_lo.view(B, T, inner))
+            pool.put(q_hi, q_lo, kv_hi, kv_lo)
+            h = project_out(w[pre + ".attn2.to_out.0"], o_hi, o_lo, h)
+            # ---- GEGLU feed-forward -----------------------------------------------------------------------------------
+            if not blk.ff.glu:
+                raise NotImplementedError("SpatialTransformer feed-forward without GEGLU")
+            n_hi, n_lo = layernorm(blk.norm3, h)
+            uu, _, _ = self._conv(pool, w[pre + ".ff.net.0.proj"], a_hi=n_hi, a_lo=n_lo, shape=(B, H, W))
+            pool.put(n_hi, n_lo)
+            ffi = uu.shape[3] // 2
+            g_hi, g_lo = pool.get((B, H, W, ffi), bf), pool.get((B, H, W, ffi), bf)
+            be.geglu_split(uu, out_hi=g_hi, out_lo=g_lo)
+            pool.put(uu)
+            h = project_out(w[pre + ".ff.net.2"], g_hi, g_lo, h)
+        r_hi, r_lo = pool.get(tok, bf), pool.get(tok, bf)
+        be.prep(h, None, resample=cabi.RESAMPLE_NONE, raw_hi=r_hi, raw_lo=r_lo)
+        pool.put(h)
+        out, _, _ = self._conv(pool, w[name + ".proj_out"], a_hi=r_hi, a_lo=r_lo, shape=(B, H, W), residual=x,
+                               res_mode=cabi.RES_SAME, stats=True)
+        pool.put(r_hi, r_lo)
+        return out
+
     def _resample_layer(self, pool, name, m, x):
         be, w = self.be, self._w
         B, H, W, Cc = x.shape
@@ -561,6 +666,8 @@ class UNetEngine(KernelExecutor):
                 assert cur_skip is None, "a concatenated input is only consumed by a ResBlock"
                 if isinstance(layer, AttentionBlock):
                     new = self._attention(pool, name, layer, cur)
+                elif isinstance(layer, SpatialTransformer):
+                    new = self._spatial_transformer(pool, name, layer, cur, self._ctx_nhwc)
                 elif isinstance(layer, (Downsample, Upsample)):
                     new = self._resample_layer(pool, name, layer, cur)
                 elif isinstance(layer, nn.Conv2d):
@@ -603,6 +710,11 @@ class UNetEngine(KernelExecutor):
         cin0 = Cx + (0 if ctx is None else ctx.shape[1])
         xin = pool.get((B, H, W, cin0))
         be.nchw_to_nhwc_cat(x, ctx, xin)
+        self._ctx_nhwc = None
+        if getattr(u, "use_spatial_transformer", False) and ctx is not None:
+            # the transformers cross-attend to the same conditioning tensor (openaimodel.py:745-748), token-major
+            self._ctx_nhwc = pool.get((B, ctx.shape[2], ctx.shape[3], ctx.shape[1]))
+            be.nchw_to_nhwc_cat(ctx, None, self._ctx_nhwc)
         hs = []
         h = xin
         for i, block in enumerate(u.input_blocks):
@@ -629,7 +741,8 @@ class UNetEngine(KernelExecutor):
             be.conv_umma(B=B, H=H, W=W, Cin=eh["cin"], Cout=64, taps=9, a_hi=a_hi, a_lo=a_lo, w_hi=eh["hi_pad"],
                          w_lo=eh["lo_pad"], bias=eh["bias_pad"], out=out, passes=self.passes,
                          out_nchw_channels=u.out_channels)
-            pool.put(a_hi, a_lo, emb, film)
+            pool.put(a_hi, a_lo, emb, film, self._ctx_nhwc)
+            self._ctx_nhwc = None
             return out
         act = pool.get(h.shape)
         be.prep(h, None, groups=GN_GROUPS, mean=mean, rstd=rstd, gamma=gn.weight.detach(), beta=gn.bias.detach(),
@@ -638,5 +751,6 @@ class UNetEngine(KernelExecutor):
         y, _, _ = self._conv(pool, eh, a_f32=act, shape=(B, H, W))
         pool.put(act)
         be.nhwc_to_nchw(y, out)
-        pool.put(y, emb, film)
+        pool.put(y, emb, film, self._ctx_nhwc)
+        self._ctx_nhwc = None
         return out

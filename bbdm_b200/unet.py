@@ -26,6 +26,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .transformer import SpatialTransformer
 from .train import (attention_core as _attention_core, conv1x1 as _conv1x1, conv2d as _conv2d,
                     gn_act_conv2d as _gn_act_conv2d, gn_conv1x1 as _gn_conv1x1)
 
@@ -68,7 +69,12 @@ class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
 
     def forward(self, x, emb, context=None):
         for layer in self:
-            x = layer(x, emb) if isinstance(layer, TimestepBlock) else layer(x)
+            if isinstance(layer, TimestepBlock):
+                x = layer(x, emb)
+            elif isinstance(layer, SpatialTransformer):
+                x = layer(x, context)
+            else:
+                x = layer(x)
         return x
 
 
@@ -222,9 +228,16 @@ class UNetModel(nn.Module):
                  use_spatial_transformer=False, transformer_depth=1, context_dim=None,
                  n_embed=None, legacy=True, condition_key="concat"):
         super().__init__()
-        if use_spatial_transformer or context_dim is not None:
-            # cross-attention conditioning is a "next" row.
-            raise NotImplementedError("use_spatial_transformer / context_dim: not on the B200 hot path yet")
+        if use_spatial_transformer:
+            assert context_dim is not None, "use_spatial_transformer needs context_dim (the conditioning's channel count)"
+        if context_dim is not None:
+            assert use_spatial_transformer, "context_dim is only used by the spatial transformer"
+            if not isinstance(context_dim, int):
+                context_dim = list(context_dim)
+                if len(context_dim) != 1:
+                    raise NotImplementedError("one context dimension per UNet is supported")
+                context_dim = int(context_dim[0])
+        self.use_spatial_transformer, self.context_dim = bool(use_spatial_transformer), context_dim
         if dims != 2 or num_classes is not None or n_embed is not None or use_fp16:
             raise NotImplementedError("only dims=2, unconditional-class, fp32 UNets are supported")
         if num_heads_upsample == -1:
@@ -250,6 +263,10 @@ class UNetModel(nn.Module):
                             use_scale_shift_norm=use_scale_shift_norm, **kw)
 
         def attn(ch, heads):
+            if use_spatial_transformer:
+                # openaimodel.py:547-564 (legacy=True): heads follow num_head_channels when given, d_head = ch // heads
+                n_heads = num_heads if num_head_channels == -1 else ch // num_head_channels
+                return SpatialTransformer(ch, n_heads, ch // n_heads, depth=transformer_depth, context_dim=context_dim)
             return AttentionBlock(ch, num_heads=heads, num_head_channels=num_head_channels,
                                   use_new_attention_order=use_new_attention_order)
 
@@ -316,10 +333,11 @@ class UNetModel(nn.Module):
         if self.condition_key != "nocond":
             x = torch.cat([x, context], dim=1)
         h, hs = x, []
+        ctx = context if self.use_spatial_transformer else None     # the transformers attend to the same 4-D context
         for i, m in enumerate(self.input_blocks):
-            h = _conv2d(m[0], h, NATIVE_TRAIN_CONV) if i == 0 else m(h, emb)     # [0] is the stem conv
+            h = _conv2d(m[0], h, NATIVE_TRAIN_CONV) if i == 0 else m(h, emb, ctx)     # [0] is the stem conv
             hs.append(h)
-        h = self.middle_block(h, emb)
+        h = self.middle_block(h, emb, ctx)
         for m in self.output_blocks:
-            h = m(torch.cat([h, hs.pop()], dim=1), emb)
+            h = m(torch.cat([h, hs.pop()], dim=1), emb, ctx)
         return _conv2d(self.out[2], self.out[1](self.out[0](h)), NATIVE_TRAIN_CONV)

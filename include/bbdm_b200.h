@@ -357,6 +357,27 @@ int bbdm_gn_bwd_apply(const float* x, const float* da, int B, int H, int W, int 
                       const float* s1, const float* s2, float* dx, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * SpatialTransformer pieces (reference base/modules/attention.py:36-264).  The 1x1 projections
+ * and every nn.Linear run on bbdm_conv_umma (taps = 1 over the [B, H, W, C] token grid); these are the remaining ops.
+ * ------------------------------------------------------------------------------------------ */
+
+/* nn.LayerNorm(C) over the last dimension of x [rows][C] (biased variance, eps inside the sqrt, affine), fp32
+ * and/or split-bf16 output (operand of the following Linear).  Replaces norm1/2/3 of BasicTransformerBlock
+ * (attention.py:203-205, 213-215).  C even, <= 2048. */
+int bbdm_layernorm_split(const float* x, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                         float* out_f32, void* out_hi, void* out_lo, void* stream);
+
+/* GEGLU gate (attention.py:36-43): u [rows][2N] = the projection's output -> out[r][n] = u[r][n] * gelu(u[r][N+n])
+ * (exact erf GELU), fp32 and/or split-bf16. */
+int bbdm_geglu_split(const float* u, int64_t rows, int N, float* out_f32, void* out_hi, void* out_lo, void* stream);
+
+/* Cross-attention core (CrossAttention.forward, attention.py:166-192): queries q [B,Tq,C] and keys|values
+ * kv [B,Tkv,2C] (k = columns [0,C), v = [C,2C)), both as split-bf16 planes, head h = columns h*D..(h+1)*D of each;
+ * out[b,i,:] = softmax_j(q_i.k_j * D^-1/2) v_j per head, flash-style (no Tq x Tkv buffer).  D in {16,32,64}. */
+int bbdm_attention_cross(const void* q_hi, const void* q_lo, const void* kv_hi, const void* kv_lo, int B, int Tq,
+                         int Tkv, int C, int heads, float* out_f32, void* out_hi, void* out_lo, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Output path of sample_to_eval
  * ------------------------------------------------------------------------------------------ */
 

@@ -273,9 +273,51 @@ def _attnblock(sd, p, x, d, new_order):
     return (xf + h).reshape(b, c, hh, ww)
 
 
-def _run_layers(sd, prefix, layers, h, emb, cfg):
+def _cross_attention(sd, p, x, context, heads):
+    # CrossAttention.forward, base/modules/attention.py:166-192 (no mask): x [B,N,dim], context [B,M,cdim] or None
+    ctx = x if context is None else context
+    q = F.linear(x, sd[p + ".to_q.weight"])
+    k = F.linear(ctx, sd[p + ".to_k.weight"])
+    v = F.linear(ctx, sd[p + ".to_v.weight"])
+    b, n, inner = q.shape
+    d = inner // heads
+    sp = lambda t: t.reshape(b, t.shape[1], heads, d).permute(0, 2, 1, 3).reshape(b * heads, t.shape[1], d)
+    q, k, v = sp(q), sp(k), sp(v)
+    sim = torch.einsum("bid,bjd->bij", q, k) * (d ** -0.5)
+    out = torch.einsum("bij,bjd->bid", sim.softmax(dim=-1), v)
+    out = out.reshape(b, heads, n, d).permute(0, 2, 1, 3).reshape(b, n, inner)
+    return F.linear(out, sd[p + ".to_out.0.weight"], sd[p + ".to_out.0.bias"])
+
+
+def _spatial_transformer(sd, p, x, context, d):
+    # SpatialTransformer.forward + BasicTransformerBlock._forward + GEGLU feed-forward
+    # (base/modules/attention.py:36-67, 196-264); GroupNorm eps 1e-6 (:79-80), LayerNorm eps 1e-5
+    b, c, hh, ww = x.shape
+    heads = d["heads"]
+    ctx = None if context is None else context.flatten(2).transpose(1, 2)       # 'b c h w -> b (h w) c'
+    h = F.group_norm(x, 32, sd[p + ".norm.weight"], sd[p + ".norm.bias"], 1e-6)
+    h = F.conv2d(h, sd[p + ".proj_in.weight"], sd[p + ".proj_in.bias"])
+    h = h.flatten(2).transpose(1, 2)
+    j = 0
+    while f"{p}.transformer_blocks.{j}.norm1.weight" in sd:
+        q = f"{p}.transformer_blocks.{j}"
+        ln = lambda t, n: F.layer_norm(t, (t.shape[-1],), sd[f"{q}.{n}.weight"], sd[f"{q}.{n}.bias"], 1e-5)
+        h = _cross_attention(sd, q + ".attn1", ln(h, "norm1"), None, heads) + h
+        h = _cross_attention(sd, q + ".attn2", ln(h, "norm2"), ctx, heads) + h
+        u = F.linear(ln(h, "norm3"), sd[q + ".ff.net.0.proj.weight"], sd[q + ".ff.net.0.proj.bias"])
+        a, gate = u.chunk(2, dim=-1)
+        h = F.linear(a * F.gelu(gate), sd[q + ".ff.net.2.weight"], sd[q + ".ff.net.2.bias"]) + h
+        j += 1
+    h = h.transpose(1, 2).reshape(b, -1, hh, ww)
+    return F.conv2d(h, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"]) + x
+
+
+def _run_layers(sd, prefix, layers, h, emb, cfg, context=None):
     for j, (kind, d) in enumerate(layers):
         p = f"{prefix}.{j}"
+        if kind == "attn" and getattr(cfg, "use_spatial_transformer", False):
+            h = _spatial_transformer(sd, p, h, context, d)
+            continue
         if kind == "conv":
             h = F.conv2d(h, sd[p + ".weight"], sd[p + ".bias"], padding=1)
         elif kind == "res":
@@ -313,12 +355,12 @@ def unet_forward(sd, cfg, x, t, context=None, prefix=""):
     h = x
     hs = []
     for i, layers in enumerate(plan["input"]):
-        h = _run_layers(sd, f"input_blocks.{i}", layers, h, emb, cfg)
+        h = _run_layers(sd, f"input_blocks.{i}", layers, h, emb, cfg, context)
         hs.append(h)
-    h = _run_layers(sd, "middle_block", plan["middle"], h, emb, cfg)
+    h = _run_layers(sd, "middle_block", plan["middle"], h, emb, cfg, context)
     for i, layers in enumerate(plan["output"]):
         h = torch.cat([h, hs.pop()], dim=1)
-        h = _run_layers(sd, f"output_blocks.{i}", layers, h, emb, cfg)
+        h = _run_layers(sd, f"output_blocks.{i}", layers, h, emb, cfg, context)
     h = F.silu(_gn(h, sd, "out.0"))
     return F.conv2d(h, sd["out.2.weight"], sd["out.2.bias"], padding=1)
 

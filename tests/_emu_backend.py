@@ -271,6 +271,41 @@ class EmuBackend:
             sp[:, 0, :, 1] = (o.reshape(B, -1, Cout) ** 2).sum(1)
         out.copy_(o)
 
+    # -- SpatialTransformer pieces ------------------------------------------------------------------------------
+    def layernorm_split(self, x, gamma, beta, eps, out_f32=None, out_hi=None, out_lo=None):
+        self.calls.append("layernorm_split")
+        assert not torch.isnan(x).any()
+        y = F.layer_norm(x, (x.shape[-1],), gamma, beta, eps)
+        if out_f32 is not None:
+            out_f32.copy_(y.reshape(out_f32.shape))
+        if out_hi is not None:
+            self._write_split(y.reshape(out_hi.shape), out_hi, out_lo)
+
+    def geglu_split(self, u, out_f32=None, out_hi=None, out_lo=None):
+        self.calls.append("geglu_split")
+        assert not torch.isnan(u).any()
+        a, g = u.chunk(2, dim=-1)
+        y = a * F.gelu(g)
+        if out_f32 is not None:
+            out_f32.copy_(y.reshape(out_f32.shape))
+        if out_hi is not None:
+            self._write_split(y.reshape(out_hi.shape), out_hi, out_lo)
+
+    def attention_cross(self, q_hi, q_lo, kv_hi, kv_lo, heads, out_f32=None, out_hi=None, out_lo=None):
+        self.calls.append("attention_cross")
+        q, kv = self._planes(q_hi, q_lo), self._planes(kv_hi, kv_lo)
+        assert not torch.isnan(q).any() and not torch.isnan(kv).any()
+        B, Tq, Cc = q.shape
+        d = Cc // heads
+        k, v = kv[..., :Cc], kv[..., Cc:]
+        sp = lambda t: t.reshape(B, t.shape[1], heads, d).permute(0, 2, 1, 3)
+        w = torch.softmax(torch.einsum("bhid,bhjd->bhij", sp(q), sp(k)) * d ** -0.5, dim=-1)
+        o = torch.einsum("bhij,bhjd->bhid", w, sp(v)).permute(0, 2, 1, 3).reshape(B, Tq, Cc)
+        if out_f32 is not None:
+            out_f32.copy_(o)
+        if out_hi is not None:
+            self._write_split(o, out_hi, out_lo)
+
     def denorm_to_uint8(self, images, to_normal, out):
         self.calls.append("denorm_to_uint8")
         x = images.detach().clone()

@@ -43,6 +43,14 @@ UNET_CONFIGS = {
                          use_scale_shift_norm=False, resblock_updown=False,
                          use_new_attention_order=True, use_spatial_transformer=False,
                          context_dim=None, condition_key="nocond"),
+    # cross-attention conditioning: SpatialTransformer blocks instead of AttentionBlocks; the
+    # transformers attend to the same 3-channel conditioning image that is concatenated to the input
+    "tiny_st": dict(image_size=16, in_channels=6, model_channels=32, out_channels=3,
+                    num_res_blocks=1, attention_resolutions=(2, 4), channel_mult=(1, 4, 8),
+                    conv_resample=True, dims=2, num_heads=8, num_head_channels=32,
+                    use_scale_shift_norm=True, resblock_updown=True,
+                    use_spatial_transformer=True, transformer_depth=1, context_dim=3,
+                    condition_key="SpatialRescaler"),
     # BASELINE configs[2..4] UNets (LBBDM-f4 / f8-variant / f16-variant):
     # 64x64 latents, condition_key nocond; f16 has attention at ds=4 (6 AttentionBlocks, T=256)
     "lbbdm_f4": dict(image_size=64, in_channels=3, model_channels=128, out_channels=3, num_res_blocks=2,

@@ -155,16 +155,21 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg1", action="store_true")
     ap.add_argument("--cfg2-only", action="store_true", help="only the full-size 256x256 fixture (~2 min CPU)")
+    ap.add_argument("--st-only", action="store_true", help="only the SpatialTransformer fixture")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     if a.cfg2_only:
         cfg2_full_size()
+        sys.exit(0)
+    if a.st_only:
+        unet_and_psample("tiny_st", 2, "tiny_st", with_loop=False)
         sys.exit(0)
     schedule_kats()
     unet_and_psample("tiny_pixel", 2, "tiny_pixel")
     unet_and_psample("tiny_latent", 3, "tiny_latent", bb_kw=dict(objective="noise", loss_type="l2"))
     unet_and_psample("tiny_variant", 2, "tiny_variant", bb_kw=dict(objective="ysubx", eta=0.5))
     unet_and_psample("mid_pixel", 2, "mid_pixel")
+    unet_and_psample("tiny_st", 2, "tiny_st", with_loop=False)          # SpatialTransformer / cross-attention UNet
     if a.cfg1:
         unet_and_psample("cfg1", 4, "cfg1", bb_kw=dict(sample_step=100), with_loop=False)
         # BASELINE configs[2..4] UNet shapes at a reduced batch (full channel widths / resolutions)

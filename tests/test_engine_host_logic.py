@@ -27,6 +27,7 @@ def build(unet_name):
     ("tiny_latent", 2e-5, True),
     ("tiny_variant", 2e-5, True),    # no scale-shift norm, conv up/down, new attention order
     ("mid_pixel", 6e-5, True),       # aligned channels: split-bf16 operand planes (2^-17 rounding)
+    ("tiny_st", 6e-5, True),         # SpatialTransformer blocks: LayerNorm / GEGLU / self- and cross-attention
 ])
 def test_engine_wiring_matches_reference_fixture(tag, tol, expect_umma):
     g = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(GOLD, tag + ".npz")).items() if v.ndim}
@@ -38,6 +39,8 @@ def test_engine_wiring_matches_reference_fixture(tag, tol, expect_umma):
     assert out.shape == g["unet_out"].shape and not torch.isnan(out).any()
     assert rel_dev(out, g["unet_out"]) < tol
     assert ("conv_umma" in be.calls) == expect_umma
+    if tag == "tiny_st":
+        assert {"layernorm_split", "geglu_split", "attention_cross"} <= set(be.calls)
     # second call: no new allocations (stable addresses for CUDA-graph replay), same result
     pool = eng._pool(g["x"].device, tuple(g["x"].shape[i] for i in (0, 2, 3)))
     nbytes = pool.bytes

@@ -464,3 +464,53 @@ def test_denorm_to_uint8_byte_exact(be, to_normal):
         ref = ref.mul_(0.5).add_(0.5).clamp_(0, 1.)
     ref = ref.mul_(255).add_(0.5).clamp_(0, 255).permute(0, 2, 3, 1).to(torch.uint8)
     assert torch.equal(out.cpu(), ref)
+
+
+# ------------------------------------------------------------------------------------ SpatialTransformer pieces
+@pytest.mark.parametrize("rows,C", [(64, 128), (1000, 256), (257, 1024), (16, 2048)])
+def test_layernorm_split(be, rows, C):
+    x = rnd((rows, C), 100, 1.3) + 0.2
+    g, b = 1 + 0.1 * rnd((C,), 101), 0.1 * rnd((C,), 102)
+    want = F.layer_norm(x.double(), (C,), g.double(), b.double(), 1e-5)
+    out = torch.empty((rows, C), device=DEV)
+    oh = torch.empty((rows, C), dtype=torch.bfloat16, device=DEV)
+    ol = torch.empty_like(oh)
+    be.layernorm_split(x.to(DEV), g.to(DEV), b.to(DEV), 1e-5, out_f32=out, out_hi=oh, out_lo=ol)
+    assert rel_dev(out, want) < 2e-6
+    h, l = O.bf16_split(out.cpu())
+    assert torch.equal(oh.float().cpu(), h) and torch.equal(ol.float().cpu(), l)
+
+
+@pytest.mark.parametrize("rows,N", [(64, 512), (333, 1024), (5, 64)])
+def test_geglu_split(be, rows, N):
+    u = rnd((rows, 2 * N), 110, 1.5)
+    a, gate = u.double().chunk(2, dim=-1)
+    want = a * F.gelu(gate)
+    out = torch.empty((rows, N), device=DEV)
+    oh = torch.empty((rows, N), dtype=torch.bfloat16, device=DEV)
+    ol = torch.empty_like(oh)
+    be.geglu_split(u.to(DEV), out_f32=out, out_hi=oh, out_lo=ol)
+    assert rel_dev(out, want) < 2e-6
+    h, l = O.bf16_split(out.cpu())
+    assert torch.equal(oh.float().cpu(), h) and torch.equal(ol.float().cpu(), l)
+
+
+@pytest.mark.parametrize("B,Tq,Tkv,heads,D", [(2, 64, 256, 4, 32), (1, 16, 4096, 2, 64), (2, 100, 77, 8, 16), (1, 256, 256, 4, 64)])
+def test_attention_cross(be, B, Tq, Tkv, heads, D):
+    """Cross-attention core (queries and keys|values from different tensors of different lengths) against the
+    reference CrossAttention expression (attention.py:178-191) in fp64."""
+    C = heads * D
+    q, kv = rnd((B, Tq, C), 120, 1.2), rnd((B, Tkv, 2 * C), 121, 1.2)
+    sp = lambda t: t.double().reshape(B, t.shape[1], heads, D).permute(0, 2, 1, 3)
+    w = torch.softmax(torch.einsum("bhid,bhjd->bhij", sp(q), sp(kv[..., :C])) * D ** -0.5, dim=-1)
+    want = torch.einsum("bhij,bhjd->bhid", w, sp(kv[..., C:])).permute(0, 2, 1, 3).reshape(B, Tq, C)
+    planes = lambda t: tuple(z.to(torch.bfloat16).to(DEV) for z in O.bf16_split(t))
+    q_hi, q_lo = planes(q)
+    kv_hi, kv_lo = planes(kv)
+    out = torch.empty((B, Tq, C), device=DEV)
+    oh = torch.empty((B, Tq, C), dtype=torch.bfloat16, device=DEV)
+    ol = torch.empty_like(oh)
+    be.attention_cross(q_hi, q_lo, kv_hi, kv_lo, heads, out_f32=out, out_hi=oh, out_lo=ol)
+    assert rel_dev(out, want) < 2e-5, rel_dev(out, want)
+    h, l = O.bf16_split(out.cpu())
+    assert torch.equal(oh.float().cpu(), h) and torch.equal(ol.float().cpu(), l)

@@ -18,6 +18,7 @@ TAGS = {
     "tiny_latent": ("tiny_latent", dict(objective="noise", loss_type="l2")),
     "tiny_variant": ("tiny_variant", dict(objective="ysubx", eta=0.5)),
     "mid_pixel": ("mid_pixel", {}),
+    "tiny_st": ("tiny_st", {}),          # SpatialTransformer / cross-attention conditioning
     "cfg1": ("cfg1", dict(sample_step=100)),
     "lbbdm_f4": ("lbbdm_f4", {}),        # BASELINE configs[2] UNet (latent 64x64x3, nocond)
     "lbbdm_f8": ("lbbdm_f8", {}),        # configs[3] UNet (64x64x4)

@@ -109,6 +109,20 @@ def test_oracle_matches_reference_fixture(tag):
     assert rel_dev(img, g["loop8_out"]) < 1e-5
 
 
+def test_oracle_spatial_transformer_matches_reference_fixture():
+    """SpatialTransformer / cross-attention UNet (use_spatial_transformer, context_dim 3): the oracle's restatement of
+    base/modules/attention.py against the fixture of the unmodified reference."""
+    g = load("tiny_st")
+    cfg = O.unet_cfg(**UNET_CONFIGS["tiny_st"])
+    sd = oracle_state("tiny_st")
+    bufs, steps = O.make_schedule()
+    x, y, t = g["x"], g["y"], g["t"]
+    assert rel_dev(O.unet_forward(sd, cfg, x, t, y), g["unet_out"]) < 2e-6
+    for i in g["ps_ids"].tolist():
+        o, _ = O.p_sample(sd, cfg, bufs, steps, i, g[f"ps{i}_xt"], y, y, g[f"ps{i}_noise"], prefix="")
+        assert rel_dev(o, g[f"ps{i}_out"]) < 2e-6
+
+
 @pytest.mark.parametrize("tag", ["cfg1", "lbbdm_f4", "lbbdm_f8", "lbbdm_f16"])
 def test_oracle_matches_full_size_fixture(tag):
     """Full-size template UNets (237-258 M parameters): BASELINE configs[0] and the UNets of configs[2..4]."""
