@@ -527,12 +527,24 @@ def main():
     peaks, peak_src = load_peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     achieved_tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
-    if os.path.exists(tp):        # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch_mean")
+    traffic = traffic_src = None
+    for tp in ("r02_conv_traffic.json", "r01_conv_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", tp)
+        if os.path.exists(tp):    # dram__bytes_read.sum + dram__bytes_write.sum per conv_umma launch, mean over the launches of
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch_mean")      # one ncu --set full capture of this command
+            traffic_src = os.path.relpath(tp, ROOT)
+            break
+    # GPU library baseline (SURVEY 8d "the real bar"): the same architecture on stock PyTorch kernels, measured by
+    # tools/bench_torchlib.py on a B200 of this pool (separate process: its fp32 row peaks at 183 GB of HBM)
+    library = None
+    lp = os.path.join(ROOT, "profiles", "r02_torch_library_baseline_%s.json" % args.config)
+    if not os.path.exists(lp):
+        lp = os.path.join(ROOT, "profiles", "r01_torch_library_baseline_%s.json" % args.config)
+    if os.path.exists(lp):
+        library = {"source": os.path.relpath(lp, ROOT) + " (tools/bench_torchlib.py, same pool, not this run)",
+                   "rows": [{k: r.get(k) for k in ("mode", "ms_per_step", "steps_per_s")} for r in json.load(open(lp)).get("rows", [])]}
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": traffic,
+                "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": "conv_umma_kernel (tcgen05 implicit-GEMM conv, %d launches/step, %d of them Winograd F(4x4,3x3) "
                           "position GEMMs whose input/output transform kernels -- %.2f ms/step -- are included in kernel_ms)"
                           % (n_conv, n_wino, wino_tf_ms),
@@ -569,7 +581,8 @@ def main():
                            "unet_tflops_per_s": world * cfg["flops_per_step"] / (ms_dev * 1e-3) / 1e12},
                 "e2e": {"value": world * 1e3 / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": 2 * nbytes,
                         "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clk}
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "gpu_library_baseline": library,
+                "clocks": clk}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -4,6 +4,7 @@ import os
 
 import pytest
 import torch
+import torch.nn.functional as F
 
 from _recipe import rel_dev
 from oracle import bbdm_oracle as O

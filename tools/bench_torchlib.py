@@ -14,7 +14,10 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
+import bbdm_b200.unet as U  # noqa: E402
 from bbdm_b200.unet import UNetModel  # noqa: E402
+
+U.NATIVE_TRAIN_CONV = False        # the module forwards on stock PyTorch kernels only (no bbdm_b200 autograd Functions)
 
 
 def run(mode, cfg, steps=3, warmup=2):
