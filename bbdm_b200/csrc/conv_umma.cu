@@ -555,7 +555,9 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   p.f16 = f16 ? 1 : 0;
   // chunk length: 4 K-blocks (direct conv); 2 for the Winograd position GEMMs, whose output transform amplifies
   // the truncation error of the TMEM accumulator (tools/studies/tmem_rz_accumulation.py)
-  p.kb_per_chunk = (wpi ? 2 : (a->passes == 3 ? 4 : 8)) * (64 / BK);
+  static int wino_chunk = 0;      // BBDM_WINO_CHUNK: K blocks per promotion chunk of the position GEMMs (A/B switch, default 2)
+  if (!wino_chunk) { const char* e = getenv("BBDM_WINO_CHUNK"); wino_chunk = (e && atoi(e) > 0) ? atoi(e) : 2; }
+  p.kb_per_chunk = (wpi ? wino_chunk : (a->passes == 3 ? 4 : 8)) * (64 / BK);
   if (wpi) BBDM_REQUIRE(p.TB == 1, "conv_umma: weights_per_image needs 128-pixel tiles inside one image (H*W >= 128)");
   p.bias = a->bias; p.bias2 = a->Cin2 ? a->bias2 : nullptr;
   p.residual = a->residual; p.res_mode = a->res_mode;

@@ -240,10 +240,13 @@ class UNetEngine(KernelExecutor):
             return
         be, u = self.be, self.unet
         dev = next(u.parameters()).device
-        # same parameter storage (in-place optimizer update): re-pack into the existing cache
-        # buffers so their addresses -- and any captured CUDA graph -- stay valid
-        old = self._w if (self._ptrs(key) == self._ptrs(self._wkey) and self._w) else {}
-        if not old:
+        # Derived caches are re-packed into the EXISTING buffers whenever name, shape and device match (no
+        # reallocation of the ~5 GB of planes when the runner swaps EMA weights in and out for validation /
+        # sampling, runners/base/EMA.py:31-43).  Same parameter storage (in-place optimizer update): every address a
+        # captured CUDA graph holds stays valid; changed storage (EMA .data swap, load_state_dict): biases / norm
+        # affines are read through the parameters' own addresses, so graphs are re-captured (generation bump).
+        old = self._w or {}
+        if self._ptrs(key) != self._ptrs(self._wkey) or not self._w:
             self.generation += 1
         w = {}
 
@@ -270,9 +273,10 @@ class UNetEngine(KernelExecutor):
                 ent["hi"], ent["lo"] = hi, lo
             elif name == "out.2" and cin % 64 == 0 and cout < 64 and k == 3:
                 # UNet head (Cout = 3..16): zero-padded to one 64-wide N tile of the tensor-core conv
-                made = not (isinstance(old.get(name), dict) and "hi_pad" in old[name])
+                prev = old[name].get("hi_pad") if isinstance(old.get(name), dict) else None
                 hi = buf(name, "hi_pad", (k * k, 64, cin), torch.bfloat16)
                 lo = buf(name, "lo_pad", (k * k, 64, cin), torch.bfloat16)
+                made = hi is not prev                 # freshly allocated: the padding rows must be zeroed
                 bp = buf(name, "bias_pad", (64,), torch.float32)
                 if made:
                     hi.zero_(); lo.zero_()
@@ -340,7 +344,7 @@ class UNetEngine(KernelExecutor):
                 pl = buf(cname, "up_lo", (16, m.out_channels, m.channels), torch.bfloat16)
                 be.pack_weight_split_taps(wp, ph, pl)
                 w[cname]["up_hi"], w[cname]["up_lo"] = ph, pl
-        if old and old.get("film_n") == off:
+        if old and old.get("film_n") == off and old["film_w"].device == dev:
             w["film_w"], w["film_b"] = old["film_w"], old["film_b"]
             torch.cat(film_w, 0, out=w["film_w"])
             torch.cat(film_b, 0, out=w["film_b"])

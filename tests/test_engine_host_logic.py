@@ -81,9 +81,15 @@ def test_weight_cache_refresh_on_param_change():
     eng.refresh_weights()
     assert be.calls.count("pack_weight_f32") == 2 * n0
     p = net.out[2].weight
+    gen = eng.generation
+    addr = {k: v["f32"].data_ptr() for k, v in eng._w.items() if isinstance(v, dict) and "f32" in v}
     p.data = p.data.clone()                                     # EMA-style .data swap
     eng.refresh_weights()
     assert be.calls.count("pack_weight_f32") == 3 * n0
+    # the derived caches are re-packed into the same buffers (no reallocation per EMA swap); captured graphs are
+    # invalidated because biases / norm affines are read through the parameters' own (changed) addresses
+    assert {k: v["f32"].data_ptr() for k, v in eng._w.items() if isinstance(v, dict) and "f32" in v} == addr
+    assert eng.generation == gen + 1
 
 
 def test_unet_rejects_cpu_inference():
