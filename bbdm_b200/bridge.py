@@ -158,7 +158,9 @@ class BridgeOps:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # explicit capture stream on THIS device: torch.cuda.graph's default capture stream is created once per
+        # process on whatever device was current then (a model on cuda:1 after one on cuda:0 captured nothing)
+        with torch.cuda.graph(graph, stream=side):
             step()
         st["graph"] = graph
         self._graphs[key] = st

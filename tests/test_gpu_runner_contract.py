@@ -100,11 +100,22 @@ def test_model_on_non_default_device_index():
     net0 = net0.to("cuda:0")
     assert torch.cuda.current_device() == 0
     y = synth_images((2, 3, 32, 32), 3)
-    torch.manual_seed(5)
-    a = net0.sample(y.to("cuda:0"), clip_denoised=False)
-    torch.manual_seed(5)
-    b = net1.sample(y.to("cuda:1"), clip_denoised=False)
+    g = torch.Generator().manual_seed(5)
+    noises = [torch.randn(2, 3, 32, 32, generator=g) for _ in range(8)]      # the same Gaussian draws on both devices
+
+    def run(net, dev):
+        it = iter(noises)
+        net._bridge.noise_source = lambda like: next(it).to(like.device)
+        return net.sample(y.to(dev), clip_denoised=False)
+
+    a = run(net0, "cuda:0")
+    b = run(net1, "cuda:1")
     assert b.device.index == 1
     net1._bridge.backend().check_fault(device="cuda:1")
-    # same kernels, same inputs, per-device Philox generators seeded alike => identical samples
+    eps1 = net1.denoise_fn(y.to("cuda:1"), timesteps=torch.tensor([7, 500], device="cuda:1"), context=y.to("cuda:1"))
+    eps0 = net0.denoise_fn(y.to("cuda:0"), timesteps=torch.tensor([7, 500], device="cuda:0"), context=y.to("cuda:0"))
+    print(f"\n[cuda:1 vs cuda:0] UNet max diff {float((eps1.cpu() - eps0.cpu()).abs().max()):.3e}; "
+          f"sample max diff {float((a.cpu() - b.cpu()).abs().max()):.3e}")
+    # same kernels, same inputs, same noise => identical results on either device
+    assert torch.equal(eps0.cpu(), eps1.cpu())
     assert torch.equal(a.cpu(), b.cpu())
