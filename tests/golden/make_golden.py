@@ -125,6 +125,30 @@ def unet_and_psample(unet_name, B, tag, bb_kw=None, step_ids=(3, -1), with_loop=
           f"{os.path.getsize(path) / 1e3:.0f} kB")
 
 
+def mid_pixel_gradients():
+    """Training step of the UNMODIFIED reference on mid_pixel (the fixture's x, y, t, q_noise): loss and the gradients
+    of a spread of parameters (stem, a ResBlock's convs / norms / FiLM linear, attention qkv + proj, time MLP, head) ->
+    mid_pixel_grads.npz.  Checked on the GPU against the native training path (tests/test_gpu_training.py)."""
+    torch.set_grad_enabled(True)
+    net = build_ref("mid_pixel").train()
+    g = np.load(os.path.join(HERE, "mid_pixel.npz"))
+    x, y, t, nz = (torch.from_numpy(g[k]) for k in ("x", "y", "t", "q_noise"))
+    loss, _ = net.p_losses(x, y, y, t, nz)
+    loss.backward()
+    names = [n for n, _ in net.denoise_fn.named_parameters()]
+    pick = [n for n in names if n.startswith(("time_embed.0", "input_blocks.0.0", "input_blocks.1.0.", "input_blocks.3.0.",
+                                               "middle_block.1.", "output_blocks.2.0.in_layers.2", "output_blocks.5.0.skip",
+                                               "out.0", "out.2"))]
+    data = {"loss": np.float32(loss.item())}
+    params = dict(net.denoise_fn.named_parameters())
+    for n in pick:
+        data["grad:" + n] = params[n].grad.detach().numpy()
+    path = os.path.join(HERE, "mid_pixel_grads.npz")
+    np.savez_compressed(path, **data)
+    torch.set_grad_enabled(False)
+    print("mid_pixel_grads", len(pick), "tensors", f"{os.path.getsize(path) / 1e3:.0f} kB")
+
+
 def cfg2_full_size(B=1):
     """BASELINE configs[1] at FULL size (256x256 pixel BBDM, 200-step schedule): UNet forward, one mid-trajectory
     and the final p_sample of the unmodified reference.  Inputs are regenerated by the tests from the same seeds
@@ -156,10 +180,14 @@ if __name__ == "__main__":
     ap.add_argument("--cfg1", action="store_true")
     ap.add_argument("--cfg2-only", action="store_true", help="only the full-size 256x256 fixture (~2 min CPU)")
     ap.add_argument("--st-only", action="store_true", help="only the SpatialTransformer fixture")
+    ap.add_argument("--grads-only", action="store_true", help="only the mid_pixel gradient fixture")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     if a.cfg2_only:
         cfg2_full_size()
+        sys.exit(0)
+    if a.grads_only:
+        mid_pixel_gradients()
         sys.exit(0)
     if a.st_only:
         unet_and_psample("tiny_st", 2, "tiny_st", with_loop=False)
@@ -170,6 +198,7 @@ if __name__ == "__main__":
     unet_and_psample("tiny_variant", 2, "tiny_variant", bb_kw=dict(objective="ysubx", eta=0.5))
     unet_and_psample("mid_pixel", 2, "mid_pixel")
     unet_and_psample("tiny_st", 2, "tiny_st", with_loop=False)          # SpatialTransformer / cross-attention UNet
+    mid_pixel_gradients()
     if a.cfg1:
         unet_and_psample("cfg1", 4, "cfg1", bb_kw=dict(sample_step=100), with_loop=False)
         # BASELINE configs[2..4] UNet shapes at a reduced batch (full channel widths / resolutions)

@@ -30,7 +30,11 @@ def run(mode, cfg, steps=3, warmup=2, ddp=False):
     B, C, S = cfg["batch"], cfg["channels"], cfg["size"]
     x = bench.synth((B, C, S, S), 1).to(dev)
     y = bench.synth((B, C, S, S), 2).to(dev)
-    opt = torch.optim.Adam(net.get_parameters(), lr=1e-4)
+    if mode == "native" and "--torch-adam" not in sys.argv:
+        from bbdm_b200.optim import FusedAdam                      # one multi-tensor launch per optimizer step
+        opt = FusedAdam(net.get_parameters(), lr=1e-4)
+    else:
+        opt = torch.optim.Adam(net.get_parameters(), lr=1e-4)
     model = net
     if ddp:      # exactly what runners/BaseRunner.py:76 does
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], output_device=dev.index)
@@ -63,7 +67,7 @@ def run(mode, cfg, steps=3, warmup=2, ddp=False):
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         extra = {"ddp_world": dist.get_world_size(), "grads_identical_across_ranks": bool(torch.equal(lo, hi))}
-    return {**extra, "mode": mode, "ms_per_micro_step": ms, "micro_steps_per_s": 1e3 / ms, "loss": float(loss),
+    return {**extra, "mode": mode, "optimizer": type(opt).__name__, "ms_per_micro_step": ms, "micro_steps_per_s": 1e3 / ms, "loss": float(loss),
             "train_tflops_per_s": 3 * cfg["flops_per_step"] / ms / 1e9, "max_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
 
 
