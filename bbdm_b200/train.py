@@ -29,6 +29,21 @@ WINO_MIN_C = int(os.environ.get("BBDM_WINO_MIN_C", "256"))
 WINO_MIN_TILES = int(os.environ.get("BBDM_WINO_MIN_TILES", "512"))
 
 
+_WARNED = set()
+
+
+def _library_path(what, x):
+    """A CUDA training call whose shape the native kernels do not take runs on stock PyTorch (library) kernels: valid
+    results, but not this library's path -- say so once per shape instead of falling back silently."""
+    if x.is_cuda:
+        key = (what, tuple(x.shape))
+        if key not in _WARNED:
+            _WARNED.add(key)
+            import warnings
+            warnings.warn(f"bbdm_b200.train: {what} with input {tuple(x.shape)} runs on stock PyTorch kernels "
+                          "(shape outside the tensor-core kernels' envelope)", stacklevel=3)
+
+
 def _wino_ok(be, B, H, W, Cin, Cout, k):
     if not WINO_TRAIN or k != 3 or min(Cin, Cout) < WINO_MIN_C or Cin % 64 or Cout % 64 or not hasattr(be, "wino_geometry"):
         return False
@@ -285,6 +300,8 @@ def gn_act_conv2d(norm, conv, x, scale=None, shift=None, enabled=True, resample=
         sc = None if scale is None else scale.reshape(scale.shape[0], -1)
         sh = None if shift is None else shift.reshape(shift.shape[0], -1)
         return GNActConv2dFn.apply(x, norm.weight, norm.bias, sc, sh, conv.weight, conv.bias, resample, residual, act)
+    if enabled:
+        _library_path("GroupNorm+activation+conv", x)
     h = norm(x)
     if scale is not None:
         h = h * (1 + scale) + shift
@@ -436,4 +453,6 @@ def conv2d(conv: torch.nn.Conv2d, x: torch.Tensor, enabled: bool = True) -> torc
         return Conv2dFn.apply(x, conv.weight, conv.bias)
     if enabled and small_ok(conv, x):
         return SmallConv2dFn.apply(x, conv.weight, conv.bias)
+    if enabled:
+        _library_path(f"Conv2d {conv.in_channels}->{conv.out_channels} k{conv.kernel_size[0]}", x)
     return conv(x)

@@ -107,7 +107,14 @@ class SpatialTransformer(nn.Module):
             [BasicTransformerBlock(inner, n_heads, d_head, dropout=dropout, context_dim=context_dim) for _ in range(depth)])
         self.proj_out = _zero(nn.Conv2d(inner, in_channels, kernel_size=1))
 
+    _warned = False
+
     def forward(self, x, context=None):
+        if x.is_cuda and not SpatialTransformer._warned:
+            SpatialTransformer._warned = True
+            import warnings
+            warnings.warn("bbdm_b200: SpatialTransformer blocks train on stock PyTorch kernels (their inference path is "
+                          "native: UNetEngine._spatial_transformer)", stacklevel=2)
         b, c, h, w = x.shape
         x_in = x
         x = self.proj_in(self.norm(x))
