@@ -33,7 +33,7 @@ SYMBOLS = [
     "bbdm_conv_wgrad_direct", "bbdm_attention_bwd", "bbdm_conv_direct_pad", "bbdm_softmax_rows_split", "bbdm_vq_nearest", "bbdm_s2d_split", "bbdm_pack_weight_split_both",
     "bbdm_wino_geometry", "bbdm_wino_input", "bbdm_wino_output", "bbdm_wino_pack_weight",
     "bbdm_optim_chunk_elems", "bbdm_adam_multi", "bbdm_ema_multi", "bbdm_denorm_to_uint8",
-    "bbdm_layernorm_split", "bbdm_geglu_split", "bbdm_attention_cross",
+    "bbdm_layernorm_split", "bbdm_geglu_split", "bbdm_attention_cross", "bbdm_conv_stem",
 ]
 
 
@@ -121,6 +121,7 @@ def load():
     lib.bbdm_pack_weight_f32.argtypes = [vp, i, i, i, vp, vp]
     lib.bbdm_conv_umma.argtypes = [C.POINTER(ConvArgs), vp]
     lib.bbdm_conv_direct.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
+    lib.bbdm_conv_stem.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp, vp]
     lib.bbdm_attention.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp]
     lib.bbdm_conv_umma_geometry.argtypes = [i, i, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     lib.bbdm_gn_finalize_partials.argtypes = [vp, i, i, vp, i, i, i, i, i, f, vp, vp, vp]
@@ -481,6 +482,12 @@ class CudaBackend:
         B, H, W, Cin = src.shape
         check(self.lib.bbdm_conv_direct(ptr(_req(src)), ptr(_req(w_packed)), ptr(bias), ptr(residual),
                                         ptr(_req(out)), B, H, W, Cin, Cout, k, stride, stream()))
+        LAUNCHES["n"] += 1
+
+    def conv_stem(self, src, w_packed, bias, out, Cout, stats_partial=None):
+        B, H, W, Cin = src.shape
+        check(self.lib.bbdm_conv_stem(ptr(_req(src)), ptr(_req(w_packed)), ptr(bias), ptr(_req(out)), B, H, W, Cin, Cout,
+                                      ptr(stats_partial), stream()))
         LAUNCHES["n"] += 1
 
     # -- attention -------------------------------------------------------------------------------

@@ -90,6 +90,84 @@ conv_direct_kernel(const float* __restrict__ src, const float* __restrict__ wp,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// UNet stem (openaimodel.py:524: Conv2d(in_channels, model_channels, 3, padding=1), Cin = 3..16): the general kernel
+// above pads its 16-channel K chunk with zeros (62 % wasted at Cin = 6) and synchronises per tap -- 1.35 ms at cfg2.
+// Here one CTA owns one image row: the whole weight set (<= 9*16*128 floats) sits in shared memory, the 3-row input
+// strip of a 32-pixel sub-tile is staged once, lane l accumulates couts l, l+32, .. for 4 pixels, and the row's
+// GroupNorm partial sums (sum, sum of squares per cout) come out of the same pass (the separate statistics pass over
+// the stem output disappears).  Same fp32 FMA order as conv_direct_kernel (tap-major, channel-minor) => identical bits.
+template <int NJ>            // couts per lane: Cout / 32 (1..4)
+__global__ void __launch_bounds__(256)
+conv_stem_kernel(const float* __restrict__ src, const float* __restrict__ wp, const float* __restrict__ bias,
+                 float* __restrict__ out, int H, int W, int Cin, float* __restrict__ stats) {
+  extern __shared__ float sm[];
+  const int Cout = NJ * 32;
+  float* ws = sm;                                   // [9*Cin][Cout]
+  float* as = sm + 9 * Cin * Cout;                  // [3][34][Cin]
+  float* red = as + 3 * 34 * Cin;                   // [8][Cout][2]
+  const int b = blockIdx.x / H, y = blockIdx.x % H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 9 * Cin * Cout; i += 256) ws[i] = wp[i];
+  float bj[NJ], ssum[NJ], ssq[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) { bj[j] = bias ? bias[lane + 32 * j] : 0.f; ssum[j] = 0.f; ssq[j] = 0.f; }
+  for (int x0 = 0; x0 < W; x0 += 32) {
+    __syncthreads();                                // previous sub-tile done with `as` (and ws loaded)
+    for (int i = threadIdx.x; i < 3 * 34 * Cin; i += 256) {
+      const int c = i % Cin, col = (i / Cin) % 34, r = i / (Cin * 34);
+      const int yy = y + r - 1, xx = x0 + col - 1;
+      as[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? src[(((int64_t)b * H + yy) * W + xx) * Cin + c] : 0.f;
+    }
+    __syncthreads();
+    float acc[4][NJ];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3, dx = tap % 3;
+      const float* arow = as + (dy * 34 + warp * 4 + dx) * Cin;
+      const float* wrow = ws + tap * Cin * Cout + lane;
+      for (int c = 0; c < Cin; ++c) {
+        float w[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) w[j] = wrow[c * Cout + 32 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a = arow[i * Cin + c];
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) acc[i][j] = fmaf(a, w[j], acc[i][j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int x = x0 + warp * 4 + i;
+      float* o = out + (((int64_t)b * H + y) * W + x) * Cout + lane;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const float v = acc[i][j] + bj[j];
+        o[32 * j] = v;
+        ssum[j] += v;
+        ssq[j] = fmaf(v, v, ssq[j]);
+      }
+    }
+  }
+  if (stats) {
+    // fixed-order combine of the 8 warps => deterministic partial sums, one row per image row
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { red[(warp * Cout + lane + 32 * j) * 2] = ssum[j]; red[(warp * Cout + lane + 32 * j) * 2 + 1] = ssq[j]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < Cout; c += 256) {
+      float a = 0.f, q = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a += red[(k * Cout + c) * 2]; q += red[(k * Cout + c) * 2 + 1]; }
+      *reinterpret_cast<float2*>(stats + ((int64_t)blockIdx.x * Cout + c) * 2) = make_float2(a, q);
+    }
+  }
+}
+
 }  // namespace bbdm
 
 using namespace bbdm;
@@ -247,3 +325,36 @@ extern "C" int bbdm_conv_wgrad_direct(const float* dy, const float* x, int B, in
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
 }
+
+// UNet stem: src [B,H,W,Cin] fp32 (Cin <= 16), w_packed [9][Cin][Cout] from bbdm_pack_weight_f32, k = 3, stride 1,
+// pad 1, Cout in {32, 64, 96, 128}, W a multiple of 32.  stats_partial (optional): [B*H][Cout][2] GroupNorm partial
+// sums of the output (rows_per_image = H for bbdm_gn_finalize_partials).
+extern "C" int bbdm_conv_stem(const float* src, const float* w_packed, const float* bias, float* out, int B, int H,
+                              int W, int Cin, int Cout, float* stats_partial, void* stream) {
+  BBDM_REQUIRE(src && w_packed && out, "conv_stem: null pointer");
+  BBDM_REQUIRE(B > 0 && H > 0 && W > 0 && W % 32 == 0 && Cin > 0 && Cin <= 16 && Cout >= 32 && Cout <= 128 && Cout % 32 == 0,
+               "conv_stem: need W %% 32 == 0, Cin <= 16, Cout in {32,64,96,128} (got W=%d Cin=%d Cout=%d)", W, Cin, Cout);
+  BBDM_REQUIRE((int64_t)B * H < (1ll << 31), "conv_stem: too many rows");
+  const size_t smem = ((size_t)9 * Cin * Cout + 3 * 34 * Cin + 8 * Cout * 2) * sizeof(float);
+  const unsigned grid = (unsigned)((int64_t)B * H);
+  cudaStream_t s = (cudaStream_t)stream;
+#define BBDM_STEM(NJ)                                                                                         \
+  {                                                                                                           \
+    static DeviceOnce cfgd;                                                                                   \
+    if (smem > 48 * 1024 && cfgd.need()) {                                                                    \
+      BBDM_CUDA_CHECK(cudaFuncSetAttribute(conv_stem_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
+      cfgd.mark();                                                                                            \
+    }                                                                                                         \
+    conv_stem_kernel<NJ><<<grid, 256, smem, s>>>(src, w_packed, bias, out, H, W, Cin, stats_partial);          \
+  }
+  switch (Cout / 32) {
+    case 1: BBDM_STEM(1) break;
+    case 2: BBDM_STEM(2) break;
+    case 3: BBDM_STEM(3) break;
+    default: BBDM_STEM(4) break;
+  }
+#undef BBDM_STEM
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+

@@ -553,6 +553,21 @@ class UNetEngine(KernelExecutor):
         pool.put(o_f32, o_hi, o_lo)
         return out
 
+    def _stem(self, pool, ent, x):
+        """A bare nn.Conv2d inside a block = the UNet stem (openaimodel.py:524): few input channels.  Dedicated kernel
+        (weights in shared memory, GroupNorm partial sums of the output fused) when the shape fits, else the general
+        fp32 kernel."""
+        B, H, W, cin = x.shape
+        cout = ent["cout"]
+        if ent["k"] == 3 and cin <= 16 and cout % 32 == 0 and cout <= 128 and W % 32 == 0 and hasattr(self.be, "conv_stem"):
+            out = pool.get((B, H, W, cout))
+            part = pool.get((B * H, cout, 2))
+            self.be.conv_stem(x, ent["f32"], ent["bias"], out, cout, stats_partial=part)
+            out._gn = (part, H)
+            return out
+        out, _, _ = self._conv(pool, ent, a_f32=x, shape=(B, H, W))
+        return out
+
     def _spatial_transformer(self, pool, name, m: SpatialTransformer, x, ctx):
         """GroupNorm(1e-6) -> proj_in -> [LN -> self-attention -> +, LN -> cross-attention(context) -> +,
         LN -> GEGLU feed-forward -> +] x depth -> proj_out -> + x   (reference attention.py:196-264).  Every Linear /
@@ -675,7 +690,7 @@ class UNetEngine(KernelExecutor):
                 elif isinstance(layer, (Downsample, Upsample)):
                     new = self._resample_layer(pool, name, layer, cur)
                 elif isinstance(layer, nn.Conv2d):
-                    new, _, _ = self._conv(pool, self._w[name], a_f32=cur, shape=cur.shape[:3])
+                    new = self._stem(pool, self._w[name], cur)
                 else:
                     raise NotImplementedError(type(layer).__name__)
             if owned:

@@ -299,6 +299,13 @@ int bbdm_conv_direct(const float* src, const float* w_packed, const float* bias,
                      const float* residual, float* out, int B, int H, int W, int Cin, int Cout,
                      int k, int stride, void* stream);
 
+/* UNet stem (openaimodel.py:524, Conv2d(in_channels, model_channels, 3, padding=1) with 3..16 input channels) as a
+ * dedicated kernel: weights resident in shared memory, one CTA per image row, and the GroupNorm partial sums of the
+ * output fused in (stats_partial [B*H][Cout][2], rows_per_image = H; may be NULL).  Same fp32 FMA order as
+ * bbdm_conv_direct => identical bits.  Needs W %% 32 == 0, Cin <= 16, Cout in {32, 64, 96, 128}. */
+int bbdm_conv_stem(const float* src, const float* w_packed, const float* bias, float* out, int B, int H, int W,
+                   int Cin, int Cout, float* stats_partial, void* stream);
+
 /* The same kernel with explicit zero padding (pad_lo before, pad_hi after, each < k): the VQGAN
  * Downsample pads (0,1,0,1) and strides by 2 (model/VQGAN/model.py:55-73).
  * out [B,Ho,Wo,Cout] with Ho = (H + pad_lo + pad_hi - k)/stride + 1. */

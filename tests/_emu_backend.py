@@ -376,6 +376,18 @@ class EmuBackend:
             o = o + residual
         out.copy_(o)
 
+    def conv_stem(self, src, w_packed, bias, out, Cout, stats_partial=None):
+        self.calls.append("conv_stem")
+        B, H, W, cin = src.shape
+        assert W % 32 == 0 and cin <= 16 and Cout % 32 == 0 and Cout <= 128
+        w = w_packed.reshape(3, 3, cin, Cout).permute(3, 2, 0, 1)
+        o = F.conv2d(src.permute(0, 3, 1, 2), w, bias, padding=1).permute(0, 2, 3, 1)
+        out.copy_(o)
+        if stats_partial is not None:
+            sp = stats_partial.view(B, H, Cout, 2)
+            sp[..., 0] = o.sum(2)
+            sp[..., 1] = (o * o).sum(2)
+
     # -- attention ----------------------------------------------------------------------------------------
     def attention(self, qkv, heads, order, out_f32=None, out_hi=None, out_lo=None):
         self.calls.append("attention")

@@ -515,3 +515,25 @@ def test_attention_cross(be, B, Tq, Tkv, heads, D):
     assert rel_dev(out, want) < 2e-5, rel_dev(out, want)
     h, l = O.bf16_split(out.cpu())
     assert torch.equal(oh.float().cpu(), h) and torch.equal(ol.float().cpu(), l)
+
+
+# ------------------------------------------------------------------------------------ stem
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 64, 6, 128), (1, 16, 32, 3, 64), (3, 8, 32, 16, 128), (2, 40, 96, 4, 32)])
+def test_conv_stem_equals_conv_direct_and_fuses_gn_partials(be, B, H, W, Cin, Cout):
+    """The dedicated stem kernel: bit-identical to the general fp32 kernel (same FMA order), and its fused GroupNorm
+    partial sums finalise to the statistics of the output."""
+    x, w, b = rnd((B, H, W, Cin), 130), rnd((Cout, Cin, 3, 3), 131, 0.05), rnd((Cout,), 132, 0.1)
+    wp = torch.empty((9, Cin, Cout), device=DEV)
+    be.pack_weight_f32(w.to(DEV), wp)
+    ref = torch.empty((B, H, W, Cout), device=DEV)
+    be.conv_direct(x.to(DEV), wp, b.to(DEV), None, ref, Cout, 3, 1)
+    out = torch.full((B, H, W, Cout), float("nan"), device=DEV)
+    part = torch.full((B * H, Cout, 2), float("nan"), device=DEV)
+    be.conv_stem(x.to(DEV), wp, b.to(DEV), out, Cout, stats_partial=part)
+    assert torch.equal(out, ref)
+    assert rel_dev(out, O.op_conv_nhwc(x.double(), w.double(), b.double())) < 2e-6
+    if Cout % 32 == 0 and Cout >= 32:
+        mean, rstd = torch.empty((B, 32), device=DEV), torch.empty((B, 32), device=DEV)
+        be.gn_finalize_partials(part, H, None, 0, B, H * W, 32, 1e-5, mean, rstd)
+        mw, rw = O.op_gn_stats(out.cpu(), 32, 1e-5)
+        assert rel_dev(mean, mw) < 1e-5 and rel_dev(rstd, rw) < 1e-5
