@@ -245,8 +245,9 @@ wino_input_smem_kernel(const WinoInParams p) {
 
   auto stage = [&](int seg, int buf) {
     const int x0 = 4 * WI_TX * seg - 1;
-    for (int px = pix0; px < NPIX; px += 16) {
-      const int i = px / WI_COLS, j = px - i * WI_COLS;
+    int i = 0, j = pix0;                                  // pix0 < 16 < WI_COLS: row 0
+    for (int px = pix0; px < NPIX; px += 16, j += 16) {
+      if (j >= WI_COLS) { j -= WI_COLS; ++i; }
       const int iy = y0 + i, ix = x0 + j;
       if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
         cp_async16(patch_s + (uint32_t)(((buf * NPIX + px) * WI_CC + ch4 * 4) * 4),
@@ -268,8 +269,9 @@ wino_input_smem_kernel(const WinoInParams p) {
     float* pb = patch + buf * WI_PATCH;
     const int x0 = 4 * WI_TX * seg - 1;
     // ---- phase 2: activate every staged pixel once, in place ------------------------------------------------
-    for (int px = pix0; px < NPIX; px += 16) {
-      const int i = px / WI_COLS, j = px - i * WI_COLS;
+    int i = 0, j = pix0;
+    for (int px = pix0; px < NPIX; px += 16, j += 16) {
+      if (j >= WI_COLS) { j -= WI_COLS; ++i; }
       const int iy = y0 + i, ix = x0 + j;
       float4* q = reinterpret_cast<float4*>(pb + px * WI_CC + ch4 * 4);
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
