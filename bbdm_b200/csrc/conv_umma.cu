@@ -555,9 +555,16 @@ extern "C" int bbdm_conv_umma(const BbdmConvArgs* a, void* stream) {
   p.f16 = f16 ? 1 : 0;
   // chunk length: 4 K-blocks (direct conv); 2 for the Winograd position GEMMs, whose output transform amplifies
   // the truncation error of the TMEM accumulator (tools/studies/tmem_rz_accumulation.py)
-  static int wino_chunk = 0;      // BBDM_WINO_CHUNK: K blocks per promotion chunk of the position GEMMs (A/B switch, default 2)
-  if (!wino_chunk) { const char* e = getenv("BBDM_WINO_CHUNK"); wino_chunk = (e && atoi(e) > 0) ? atoi(e) : 2; }
-  p.kb_per_chunk = (wpi ? wino_chunk : (a->passes == 3 ? 4 : 8)) * (64 / BK);
+  // Winograd position GEMMs: the output transform amplifies the truncation error of the TMEM accumulator, so they
+  // promote more often than the direct conv -- every 2 K-blocks below 512 input channels, every 4 from 512 on
+  // (measured chain deviation from the fp64 conv, tests/test_gpu_winograd.py: C = 256: 7.6e-6 with 2, 1.4e-5 with 4;
+  // C = 1024: 3.9e-6 with 2, 6.2e-6 with 4; model fixtures unchanged at 1.9-2.4e-5; draining 128 KB of TMEM per chunk
+  // costs ~2000 cycles of tcgen05.ld against 3072 / 6144 cycles of MMAs, so 4 is 10-15 % faster).
+  // BBDM_WINO_CHUNK overrides (A/B switch).
+  static int wino_chunk = -1;
+  if (wino_chunk < 0) { const char* e = getenv("BBDM_WINO_CHUNK"); wino_chunk = (e && atoi(e) > 0) ? atoi(e) : 0; }
+  const int wchunk = wino_chunk ? wino_chunk : (a->Cin >= 512 ? 4 : 2);
+  p.kb_per_chunk = (wpi ? wchunk : (a->passes == 3 ? 4 : 8)) * (64 / BK);
   if (wpi) BBDM_REQUIRE(p.TB == 1, "conv_umma: weights_per_image needs 128-pixel tiles inside one image (H*W >= 128)");
   p.bias = a->bias; p.bias2 = a->Cin2 ? a->bias2 : nullptr;
   p.residual = a->residual; p.res_mode = a->res_mode;
