@@ -33,7 +33,7 @@ SYMBOLS = [
     "bbdm_conv_wgrad_direct", "bbdm_attention_bwd", "bbdm_conv_direct_pad", "bbdm_softmax_rows_split", "bbdm_vq_nearest", "bbdm_s2d_split", "bbdm_pack_weight_split_both",
     "bbdm_wino_geometry", "bbdm_wino_input", "bbdm_wino_output", "bbdm_wino_pack_weight",
     "bbdm_optim_chunk_elems", "bbdm_adam_multi", "bbdm_ema_multi", "bbdm_denorm_to_uint8",
-    "bbdm_layernorm_split", "bbdm_geglu_split", "bbdm_attention_cross", "bbdm_conv_stem",
+    "bbdm_layernorm_split", "bbdm_geglu_split", "bbdm_attention_cross", "bbdm_conv_stem", "bbdm_spatial_rescale",
 ]
 
 
@@ -144,6 +144,7 @@ def load():
     lib.bbdm_wino_output.argtypes = [C.POINTER(WinoOutputArgs), vp]
     lib.bbdm_wino_pack_weight.argtypes = [vp, i, i, i, vp, vp, vp]
     lib.bbdm_denorm_to_uint8.argtypes = [vp, i, i, i, i, i, vp, vp]
+    lib.bbdm_spatial_rescale.argtypes = [vp, i, i, i, i, i, vp, vp, i, vp, vp]
     lib.bbdm_layernorm_split.argtypes = [vp, i64, i, vp, vp, f, vp, vp, vp, vp]
     lib.bbdm_geglu_split.argtypes = [vp, i64, i, vp, vp, vp, vp]
     lib.bbdm_attention_cross.argtypes = [vp, vp, vp, vp, i, i, i, i, i, vp, vp, vp, vp]
@@ -412,6 +413,15 @@ class CudaBackend:
         B, Cc, H, W = images.shape
         check(self.lib.bbdm_denorm_to_uint8(ptr(_req(images)), B, Cc, H, W, int(to_normal), ptr(_req(out, torch.uint8)),
                                             stream()))
+        LAUNCHES["n"] += 1
+
+    def spatial_rescale(self, src, n_stages, weight, bias, out):
+        """src [B,C,H,W] -> n_stages x bilinear(0.5) -> optional 1x1 map (weight [Cout,C], bias) -> out NCHW."""
+        B, Cc, H, W = src.shape
+        cout = 0 if weight is None else int(weight.shape[0])
+        check(self.lib.bbdm_spatial_rescale(ptr(_req(src)), B, Cc, H, W, int(n_stages),
+                                            ptr(None if weight is None else _req(weight)),
+                                            ptr(None if bias is None else _req(bias)), cout, ptr(_req(out)), stream()))
         LAUNCHES["n"] += 1
 
     # -- multi-tensor optimizer / EMA -----------------------------------------------------------------------

@@ -304,6 +304,53 @@ denorm_to_uint8_kernel(const float* __restrict__ x, int C, int64_t HW, int to_no
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// SpatialRescaler (encoders/modules.py:106-134): n x bilinear interpolate(scale 0.5) + optional 1x1 channel map.
+// At scale 0.5 (align_corners=False) the source coordinate of output pixel d is 2d + 0.5: both interpolation weights
+// are exactly 0.5, so one stage is h0*(w0*a + w1*b) + h1*(w0*c + w1*d) over the 2x2 block -- the products by 0.5 are
+// exact, the three additions round.  n stages = the same expression applied recursively (sizes floor-halved per
+// stage, so a level-L pixel always finds its 2x2 block inside the level-(L-1) image).
+template <int L>
+__device__ __forceinline__ float half_block(const float* __restrict__ p, int W0, int y, int x) {
+  if constexpr (L == 0) {
+    return p[(int64_t)y * W0 + x];
+  } else {
+    const float a = half_block<L - 1>(p, W0, 2 * y, 2 * x), b = half_block<L - 1>(p, W0, 2 * y, 2 * x + 1);
+    const float c = half_block<L - 1>(p, W0, 2 * y + 1, 2 * x), d = half_block<L - 1>(p, W0, 2 * y + 1, 2 * x + 1);
+    return __fadd_rn(__fmul_rn(0.5f, __fadd_rn(__fmul_rn(0.5f, a), __fmul_rn(0.5f, b))),
+                     __fmul_rn(0.5f, __fadd_rn(__fmul_rn(0.5f, c), __fmul_rn(0.5f, d))));
+  }
+}
+
+constexpr int RESCALE_MAX_C = 16;
+
+template <int L>
+__global__ void __launch_bounds__(128)
+spatial_rescale_kernel(const float* __restrict__ src, int C, int H0, int W0, int Ho, int Wo,
+                       const float* __restrict__ w, const float* __restrict__ bias, int Cout,
+                       float* __restrict__ out) {
+  const int b = blockIdx.z, y = blockIdx.y, x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= Wo) return;
+  float v[RESCALE_MAX_C];
+#pragma unroll
+  for (int c = 0; c < RESCALE_MAX_C; ++c)
+    if (c < C) v[c] = half_block<L>(src + ((int64_t)b * C + c) * H0 * W0, W0, y, x);
+  const int64_t plane = (int64_t)Ho * Wo, o = (int64_t)y * Wo + x;
+  if (w == nullptr) {
+#pragma unroll
+    for (int c = 0; c < RESCALE_MAX_C; ++c)
+      if (c < C) out[((int64_t)b * C + c) * plane + o] = v[c];
+    return;
+  }
+  for (int co = 0; co < Cout; ++co) {
+    float acc = bias ? bias[co] : 0.0f;
+#pragma unroll
+    for (int c = 0; c < RESCALE_MAX_C; ++c)
+      if (c < C) acc = fmaf(w[co * C + c], v[c], acc);
+    out[((int64_t)b * Cout + co) * plane + o] = acc;
+  }
+}
+
 }  // namespace bbdm
 
 using namespace bbdm;
@@ -482,6 +529,31 @@ int bbdm_denorm_to_uint8(const float* images, int B, int C, int H, int W, int to
   const int64_t HW = (int64_t)H * W;
   dim3 grid(grid_for(HW, 256, num_sms() * 8), B);
   denorm_to_uint8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(images, C, HW, to_normal, out);
+  BBDM_LAUNCH_CHECK();
+  return BBDM_OK;
+}
+
+/* SpatialRescaler: src [B,C,H,W] fp32 -> n_stages x bilinear(0.5) -> optional 1x1 map (w [Cout,C], bias [Cout] or NULL)
+ * -> out [B, Cout or C, H >> n, W >> n] fp32 (NCHW, what the UNet stem concatenates). */
+int bbdm_spatial_rescale(const float* src, int B, int C, int H, int W, int n_stages, const float* w, const float* bias,
+                         int Cout, float* out, void* stream) {
+  BBDM_REQUIRE(src && out && B > 0 && B <= 65535 && C > 0 && C <= RESCALE_MAX_C && H > 0 && W > 0,
+               "spatial_rescale: bad args (need 0 < C <= %d)", RESCALE_MAX_C);
+  BBDM_REQUIRE(n_stages >= 0 && n_stages <= 4, "spatial_rescale: n_stages %d not in [0, 4]", n_stages);
+  BBDM_REQUIRE(w != nullptr || bias == nullptr, "spatial_rescale: bias without weights");
+  BBDM_REQUIRE(w == nullptr || Cout > 0, "spatial_rescale: Cout must be > 0 with a channel map");
+  int Ho = H, Wo = W;
+  for (int i = 0; i < n_stages; ++i) { Ho /= 2; Wo /= 2; }
+  BBDM_REQUIRE(Ho > 0 && Wo > 0 && Ho <= 65535, "spatial_rescale: %dx%d is too small for %d stages", H, W, n_stages);
+  dim3 grid((Wo + 127) / 128, Ho, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (n_stages) {
+    case 0: spatial_rescale_kernel<0><<<grid, 128, 0, st>>>(src, C, H, W, Ho, Wo, w, bias, Cout, out); break;
+    case 1: spatial_rescale_kernel<1><<<grid, 128, 0, st>>>(src, C, H, W, Ho, Wo, w, bias, Cout, out); break;
+    case 2: spatial_rescale_kernel<2><<<grid, 128, 0, st>>>(src, C, H, W, Ho, Wo, w, bias, Cout, out); break;
+    case 3: spatial_rescale_kernel<3><<<grid, 128, 0, st>>>(src, C, H, W, Ho, Wo, w, bias, Cout, out); break;
+    default: spatial_rescale_kernel<4><<<grid, 128, 0, st>>>(src, C, H, W, Ho, Wo, w, bias, Cout, out); break;
+  }
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
 }

@@ -95,8 +95,9 @@ class FusedAdam(torch.optim.Adam):
     backend_factory = staticmethod(lambda: cabi.CudaBackend())
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, **kw):
-        if amsgrad or kw.get("maximize") or kw.get("capturable") or kw.get("differentiable"):
-            raise NotImplementedError("FusedAdam: amsgrad / maximize / capturable / differentiable are not implemented")
+        if amsgrad or any(kw.get(k) for k in ("maximize", "capturable", "differentiable", "decoupled_weight_decay")):
+            raise NotImplementedError("FusedAdam: amsgrad / maximize / capturable / differentiable / "
+                                      "decoupled_weight_decay are not implemented")
         kw.pop("foreach", None)
         kw.pop("fused", None)
         super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, **kw)

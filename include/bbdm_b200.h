@@ -384,6 +384,15 @@ int bbdm_geglu_split(const float* u, int64_t rows, int N, float* out_f32, void* 
 int bbdm_attention_cross(const void* q_hi, const void* q_lo, const void* kv_hi, const void* kv_lo, int B, int Tq,
                          int Tkv, int C, int heads, float* out_f32, void* out_hi, void* out_lo, void* stream);
 
+/* SpatialRescaler, the latent model's cond-stage encoder (model/BrownianBridge/base/modules/encoders/modules.py:106-134:
+ * n_stages x F.interpolate(scale_factor=0.5, mode='bilinear') then an optional 1x1 Conv2d channel_mapper), no-grad path,
+ * one launch.  src [B,C,H,W] fp32 (C <= 16); w [Cout,C] / bias [Cout] or NULL (no channel map: Cout ignored);
+ * out [B, Cout or C, H >> n_stages, W >> n_stages] fp32 NCHW -- the `context` the UNet stem concatenates
+ * (openaimodel.py:741-744).  0 <= n_stages <= 4.  Each stage is the exact 2x2 expression of the bilinear kernel at
+ * scale 0.5 (both weights 0.5). */
+int bbdm_spatial_rescale(const float* src, int B, int C, int H, int W, int n_stages, const float* w, const float* bias,
+                         int Cout, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Output path of sample_to_eval
  * ------------------------------------------------------------------------------------------ */

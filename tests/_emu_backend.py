@@ -313,6 +313,20 @@ class EmuBackend:
             x = x.mul_(0.5).add_(0.5).clamp_(0, 1.)
         out.copy_(x.mul_(255).add_(0.5).clamp_(0, 255).permute(0, 2, 3, 1).to(torch.uint8))
 
+    def spatial_rescale(self, src, n_stages, weight, bias, out):
+        self.calls.append("spatial_rescale")
+        x = src.detach()
+        for _ in range(n_stages):
+            h2, w2 = x.shape[2] // 2, x.shape[3] // 2
+            a, b = x[:, :, 0:2 * h2:2, 0:2 * w2:2], x[:, :, 0:2 * h2:2, 1:2 * w2:2]
+            c, d = x[:, :, 1:2 * h2:2, 0:2 * w2:2], x[:, :, 1:2 * h2:2, 1:2 * w2:2]
+            x = 0.5 * (0.5 * a + 0.5 * b) + 0.5 * (0.5 * c + 0.5 * d)
+        if weight is not None:
+            x = torch.einsum("oc,bchw->bohw", weight.detach(), x)
+            if bias is not None:
+                x = x + bias.detach().view(1, -1, 1, 1)
+        out.copy_(x)
+
     # -- multi-tensor optimizer / EMA (flat state buffers) ----------------------------------------------------
     def optim_chunk_elems(self):
         return 4096

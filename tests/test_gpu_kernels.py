@@ -467,6 +467,46 @@ def test_denorm_to_uint8_byte_exact(be, to_normal):
     assert torch.equal(out.cpu(), ref)
 
 
+# ------------------------------------------------------------------------------------ cond stage
+@pytest.mark.parametrize("n_stages,cout,bias,shape", [
+    (2, 3, False, (4, 3, 256, 256)), (1, None, False, (2, 3, 37, 51)), (3, 8, True, (2, 5, 40, 72)),
+    (0, 4, True, (1, 3, 9, 7)), (4, 16, False, (1, 16, 64, 96))])
+def test_spatial_rescale(be, n_stages, cout, bias, shape):
+    """bbdm_spatial_rescale against the reference's op chain (encoders/modules.py:124-131) on stock CUDA kernels
+    (fp32, TF32 off): interpolation stages bit-for-bit class (both weights are exactly 0.5), 1x1 map to rounding."""
+    x = rnd(shape, 95, 1.2).to(DEV)
+    w = None if cout is None else rnd((cout, shape[1]), 96, 0.5).to(DEV)
+    b = rnd((cout,), 97, 0.3).to(DEV) if bias else None
+    want = x
+    for _ in range(n_stages):
+        want = F.interpolate(want, scale_factor=0.5, mode="bilinear")
+    if w is not None:
+        want = torch.einsum("oc,bchw->bohw", w.double(), want.double()) + (0 if b is None else b.double().view(1, -1, 1, 1))
+    out = torch.empty((shape[0], shape[1] if w is None else cout, shape[2] >> n_stages, shape[3] >> n_stages), device=DEV)
+    be.spatial_rescale(x, n_stages, w, b, out)
+    assert out.shape == want.shape
+    dev = float((out.double() - want.double()).abs().max() / want.double().abs().max())
+    print(f"spatial_rescale n={n_stages} cout={cout}: rel dev {dev:.3e}")
+    assert dev <= 1e-6
+    if w is None:
+        assert (out - want).abs().max() <= 2.4e-7 * float(want.abs().max())
+
+
+def test_spatial_rescaler_module_native_path():
+    """cond.SpatialRescaler under no_grad on CUDA == its own autograd (stock) path."""
+    from bbdm_b200 import cabi
+    from bbdm_b200.cond import SpatialRescaler
+    torch.manual_seed(3)
+    m = SpatialRescaler(n_stages=2, in_channels=3, out_channels=3).to(DEV).eval()
+    x = rnd((4, 3, 128, 128), 98).to(DEV)
+    n0 = cabi.LAUNCHES["n"]
+    with torch.no_grad():
+        got = m(x)
+    assert cabi.LAUNCHES["n"] == n0 + 1
+    want = m(x).detach()                                     # grad enabled: stock ops
+    assert (got - want).abs().max() <= 1e-6 * float(want.abs().max())
+
+
 # ------------------------------------------------------------------------------------ SpatialTransformer pieces
 @pytest.mark.parametrize("rows,C", [(64, 128), (1000, 256), (257, 1024), (16, 2048)])
 def test_layernorm_split(be, rows, C):
