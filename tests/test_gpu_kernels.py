@@ -503,8 +503,12 @@ def test_spatial_rescaler_module_native_path():
     with torch.no_grad():
         got = m(x)
     assert cabi.LAUNCHES["n"] == n0 + 1
-    want = m(x).detach()                                     # grad enabled: stock ops
-    assert (got - want).abs().max() <= 1e-6 * float(want.abs().max())
+    want = x                                                 # the module's stock chain, channel map in fp64 (cuDNN
+    for _ in range(2):                                       # would run the 1x1 conv in TF32 by default)
+        want = F.interpolate(want, scale_factor=0.5, mode="bilinear")
+    want = F.conv2d(want.double(), m.channel_mapper.weight.detach().double())
+    assert got.shape == want.shape == (4, 3, 32, 32)
+    assert (got.double() - want).abs().max() <= 1e-6 * float(want.abs().max())
 
 
 # ------------------------------------------------------------------------------------ SpatialTransformer pieces
