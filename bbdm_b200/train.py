@@ -185,8 +185,16 @@ def _conv_backward(be, ctx_shape, a_hi, a_lo, weight, dy, need_dx, need_dw, need
     be.split_grad(dyn, g_hi, g_lo, gt_hi, gt_lo, dbias, ws_b)
     dxn = None
     if wino_dx:
-        # data gradient = conv of dY with the flipped, channel-swapped kernel -- on the Winograd path
-        dxn = _wino_conv(be, dyn.contiguous(), weight, dgrad=True, out_channels=Cin)
+        # data gradient = conv of dY with the flipped, channel-swapped kernel -- on the Winograd path.
+        # Its operand planes are fp16 pairs (5 exponent bits): loss gradients (1e-4 ... 1e-8) would sit in fp16's
+        # subnormal range and lose their mantissa (measured: 4e-3 per layer on the LBBDM-f4 UNet).  dY is therefore
+        # normalised by a power of two that puts its largest element into [16, 32) -- the range the forward path's
+        # activations live in -- and the result is scaled back; both scalings are exact, and the scale stays on the
+        # device (no host synchronisation).
+        amax = dyn.abs().amax().clamp_min(2.0 ** -100)
+        scale = torch.exp2(4.0 - torch.floor(torch.log2(amax)))
+        dxn = _wino_conv(be, (dyn * scale).contiguous(), weight, dgrad=True, out_channels=Cin)
+        dxn.mul_(1.0 / scale)
     elif need_dx:
         # data gradient = the same conv with the kernel flipped and Cin/Cout swapped
         wd_hi, wd_lo = wd

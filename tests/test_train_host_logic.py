@@ -48,11 +48,12 @@ def test_conv2d_function(emu, k, bias):
     assert {"pack_weight_split_both", "conv_umma", "split_grad", "conv_wgrad"} <= set(emu.calls)
 
 
-@pytest.mark.parametrize("film", [True, False])
-def test_gn_act_conv_function_winograd_route(emu, film, monkeypatch):
+@pytest.mark.parametrize("film,gscale", [(True, 0.2), (False, 0.2), (True, 3e-7)])
+def test_gn_act_conv_function_winograd_route(emu, film, gscale, monkeypatch):
     """Forward and data gradient on the Winograd path (input transform that also emits the activated split planes for
     the weight gradient, 36 position GEMMs, output transform with bias + residual; dY transformed in identity mode with
-    the flipped / channel-swapped kernel), forced on for a 64-channel 32x32 case (128 tiles)."""
+    the flipped / channel-swapped kernel), forced on for a 64-channel 32x32 case (128 tiles).  gscale 3e-7 is the
+    magnitude of real loss gradients: below fp16's normal range unless dY is normalised before the transform."""
     from bbdm_b200 import train
     from bbdm_b200.train import GNActConv2dFn
     monkeypatch.setattr(train, "WINO_MIN_C", 64)
@@ -64,7 +65,7 @@ def test_gn_act_conv_function_winograd_route(emu, film, monkeypatch):
     shift = (0.3 * rnd((B, C), 14)).requires_grad_(True) if film else None
     w, b = rnd((Cout, C, 3, 3), 15, 0.05).requires_grad_(True), rnd((Cout,), 16, 0.1).requires_grad_(True)
     res = rnd((B, Cout, H, W), 18).requires_grad_(True) if film else None
-    gy = rnd((B, Cout, H, W), 17, 0.2)
+    gy = rnd((B, Cout, H, W), 17, gscale)
     y = GNActConv2dFn.apply(x, gamma, beta, scale, shift, w, b, 0, res, True)
     y.backward(gy)
     assert emu.calls.count("wino_input") == 2 and emu.calls.count("wino_output") == 2 and "conv_wgrad" in emu.calls
@@ -159,11 +160,18 @@ def test_small_conv_function(emu):
         assert rel_dev(a.grad, r.grad) < 1e-5
 
 
-def test_training_step_host_logic_matches_torch_graph(emu, monkeypatch):
+@pytest.mark.parametrize("force_winograd", [False, True])
+def test_training_step_host_logic_matches_torch_graph(emu, monkeypatch, force_winograd):
     """One full training step of the tensor-core-aligned small UNet: every native Function (conv, GN+act+conv with
-    FiLM / resampling / fused skip, attention block) wired by unet.py vs the stock-PyTorch graph of the same modules."""
+    FiLM / resampling / fused skip, attention block) wired by unet.py vs the stock-PyTorch graph of the same modules.
+    force_winograd: the 3x3 convs of the two upper levels take the Winograd route (forward and data gradient) with the
+    model's REAL gradient magnitudes (1e-4 and below -- the case a unit-scale dY never exercises)."""
     import bbdm_b200.unet as U
+    from bbdm_b200 import train
     from bbdm_b200.bridge import BridgeOps
+    if force_winograd:
+        monkeypatch.setattr(train, "WINO_MIN_C", 64)
+        monkeypatch.setattr(train, "WINO_MIN_TILES", 16)
     from model.BrownianBridge.BrownianBridgeModel import BrownianBridgeModel
     monkeypatch.setattr(BridgeOps, "backend_factory", staticmethod(lambda: emu))          # q_sample
     g = {k: torch.from_numpy(v) if v.ndim else v for k, v in np.load(os.path.join(os.path.dirname(__file__), "golden", "mid_pixel.npz")).items()}
@@ -181,6 +189,7 @@ def test_training_step_host_logic_matches_torch_graph(emu, monkeypatch):
         res[native] = (float(loss.detach()), {n: p.grad.detach().clone() for n, p in net.denoise_fn.named_parameters()}, set(emu.calls))
     U.NATIVE_TRAIN_CONV = True
     assert {"conv_umma", "conv_wgrad", "gn_bwd_reduce", "gn_bwd_apply", "attention_bwd", "conv_wgrad_direct"} <= res[True][2]
+    assert ("wino_input" in res[True][2]) == force_winograd
     assert not ({"conv_umma", "conv_wgrad"} & res[False][2])
     assert abs(res[True][0] - float(g["loss"])) < 2e-4 * abs(float(g["loss"]))          # reference-generated loss
     worst = max(rel_dev(res[True][1][n], res[False][1][n]) for n in res[False][1])

@@ -84,7 +84,10 @@ if __name__ == "__main__":
         dist.destroy_process_group()
         sys.exit(0)
     out = {"config": cfg["name"], "what": "UNet training micro-step incl. Adam; train_tflops = 3 x forward FLOPs / time", "rows": []}
-    for mode in ("native", "fp32", "tf32", "bf16"):
+    modes = ("native", "fp32", "tf32", "bf16")
+    if "--modes" in sys.argv:
+        modes = tuple(sys.argv[sys.argv.index("--modes") + 1].split(","))
+    for mode in modes:
         try:
             out["rows"].append(run(mode, cfg))
         except Exception as e:  # noqa: BLE001
