@@ -349,7 +349,13 @@ struct WinoOutParams {
 };
 
 // One CTA per (64-channel group, tile row ty, sample b): 32 channel pairs x 8 tile-column lanes.
-__global__ void __launch_bounds__(256)
+// RES is a template parameter: the residual values of a tile are fetched as ONE batch of independent loads right after
+// the 36 loads of M (a load placed between the stores of the result cannot be moved ahead of them by the compiler --
+// `out` may alias `residual` -- and serialises 16 load -> add -> store round trips per tile: the first version ran the
+// "+ skip" layers 2.5x slower than the plain ones, profiles/r02_conv_layers_cfg2_closing.md), and the variant without a
+// residual keeps its register budget.
+template <int RES>
+__global__ void __launch_bounds__(256, 2)
 wino_output_kernel(const WinoOutParams p) {
   __shared__ float red[8][64][2];
   const int cg = blockIdx.x, ty = blockIdx.y, b = blockIdx.z;
@@ -367,6 +373,37 @@ wino_output_kernel(const WinoOutParams p) {
       const float2 v = *reinterpret_cast<const float2*>(p.m + ((int64_t)q * p.Mtot + m) * p.Cout + c);
       mx[q] = v.x; my[q] = v.y;
     }
+    // residual of the 4x4 output pixels (same / nearest-up / 2x2-average addressed), same summation order as before
+    constexpr int NRES = RES == BBDM_RES_NONE ? 1 : (RES == BBDM_RES_UP2 ? 4 : 16);
+    float2 rs[NRES];
+    if constexpr (RES == BBDM_RES_SAME) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          rs[i * 4 + j] = *reinterpret_cast<const float2*>(
+              p.residual + (((int64_t)b * p.H + 4 * ty + i) * p.W + 4 * tx + j) * p.Cout + c);
+    } else if constexpr (RES == BBDM_RES_UP2) {
+      // output pixels (4ty+i, 4tx+j) read source pixel (2ty + i/2, 2tx + j/2): 2x2 distinct values per tile
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          rs[i * 2 + j] = *reinterpret_cast<const float2*>(
+              p.residual + (((int64_t)b * (p.H >> 1) + 2 * ty + i) * (p.W >> 1) + 2 * tx + j) * p.Cout + c);
+    } else if constexpr (RES == BBDM_RES_DOWN2) {
+      const int64_t W2 = (int64_t)p.W * 2;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float* rp = p.residual + (((int64_t)b * p.H * 2 + (4 * ty + i) * 2) * W2 + (4 * tx + j) * 2) * p.Cout + c;
+          const float2 t0 = *reinterpret_cast<const float2*>(rp), t1 = *reinterpret_cast<const float2*>(rp + p.Cout);
+          const float2 t2 = *reinterpret_cast<const float2*>(rp + W2 * p.Cout);
+          const float2 t3 = *reinterpret_cast<const float2*>(rp + (W2 + 1) * p.Cout);
+          rs[i * 4 + j] = make_float2(0.25f * (((t0.x + t1.x) + t2.x) + t3.x), 0.25f * (((t0.y + t1.y) + t2.y) + t3.y));
+        }
+    }
     // Y = A^T M A: columns (6 -> 4 rows), then rows (6 -> 4 columns)
     float tx4[24], ty4[24], yx[16], yy[16];
 #pragma unroll
@@ -380,21 +417,10 @@ wino_output_kernel(const WinoOutParams p) {
       for (int j = 0; j < 4; ++j) {
         const int ww = 4 * tx + j;
         float r0 = fmaf(yx[i * 4 + j], inv, bv.x), r1 = fmaf(yy[i * 4 + j], inv, bv.y);
-        if (p.res_mode == BBDM_RES_SAME) {
-          const float2 t = *reinterpret_cast<const float2*>(p.residual + (((int64_t)b * p.H + hh) * p.W + ww) * p.Cout + c);
-          r0 += t.x; r1 += t.y;
-        } else if (p.res_mode == BBDM_RES_UP2) {
-          const float2 t = *reinterpret_cast<const float2*>(
-              p.residual + (((int64_t)b * (p.H >> 1) + (hh >> 1)) * (p.W >> 1) + (ww >> 1)) * p.Cout + c);
-          r0 += t.x; r1 += t.y;
-        } else if (p.res_mode == BBDM_RES_DOWN2) {
-          const int64_t W2 = (int64_t)p.W * 2;
-          const float* rp = p.residual + (((int64_t)b * p.H * 2 + hh * 2) * W2 + ww * 2) * p.Cout + c;
-          const float2 t0 = *reinterpret_cast<const float2*>(rp), t1 = *reinterpret_cast<const float2*>(rp + p.Cout);
-          const float2 t2 = *reinterpret_cast<const float2*>(rp + W2 * p.Cout);
-          const float2 t3 = *reinterpret_cast<const float2*>(rp + (W2 + 1) * p.Cout);
-          r0 += 0.25f * (((t0.x + t1.x) + t2.x) + t3.x);
-          r1 += 0.25f * (((t0.y + t1.y) + t2.y) + t3.y);
+        if constexpr (RES == BBDM_RES_SAME || RES == BBDM_RES_DOWN2) {
+          r0 += rs[i * 4 + j].x; r1 += rs[i * 4 + j].y;
+        } else if constexpr (RES == BBDM_RES_UP2) {
+          r0 += rs[(i >> 1) * 2 + (j >> 1)].x; r1 += rs[(i >> 1) * 2 + (j >> 1)].y;
         }
         *reinterpret_cast<float2*>(p.out + (((int64_t)b * p.H + hh) * p.W + ww) * p.Cout + c) = make_float2(r0, r1);
         sum0 += r0; sum1 += r1;
@@ -557,7 +583,13 @@ int bbdm_wino_output(const BbdmWinoOutputArgs* a, void* stream) {
   p.bias = a->bias; p.residual = a->residual; p.res_mode = a->res_mode;
   p.out = a->out; p.stats = a->stats_partial;
   dim3 grid(p.Cout / 64, p.th, p.B);
-  wino_output_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (p.res_mode) {
+    case BBDM_RES_SAME: wino_output_kernel<BBDM_RES_SAME><<<grid, 256, 0, st>>>(p); break;
+    case BBDM_RES_UP2: wino_output_kernel<BBDM_RES_UP2><<<grid, 256, 0, st>>>(p); break;
+    case BBDM_RES_DOWN2: wino_output_kernel<BBDM_RES_DOWN2><<<grid, 256, 0, st>>>(p); break;
+    default: wino_output_kernel<BBDM_RES_NONE><<<grid, 256, 0, st>>>(p); break;
+  }
   BBDM_LAUNCH_CHECK();
   return BBDM_OK;
 }
