@@ -42,7 +42,7 @@ __device__ __forceinline__ void wino_bt6(float* d) {
 }
 // A^T (4x6) applied to m[0..5] (stride S) -> y[0..3] (stride T)
 template <int S, int T>
-__device__ __forceinline__ void wino_at6(const float* m, float* y) {
+__host__ __device__ __forceinline__ void wino_at6(const float* m, float* y) {
   const float s12 = m[S] + m[2 * S], d12 = m[S] - m[2 * S];
   const float s34 = m[3 * S] + m[4 * S], d34 = m[3 * S] - m[4 * S];
   y[0] = (m[0] + s12) + s34;
@@ -354,6 +354,75 @@ struct WinoOutParams {
 // `out` may alias `residual` -- and serialises 16 load -> add -> store round trips per tile: the first version ran the
 // "+ skip" layers 2.5x slower than the plain ones, profiles/r02_conv_layers_cfg2_closing.md), and the variant without a
 // residual keeps its register budget.
+// One output tile (4x4 pixels) of one channel pair.  __host__ __device__: tools/host_check_wino_output.cu runs exactly
+// this code on the CPU against a direct fp64 evaluation (tests/test_wino_output_host.py).
+template <int RES>
+__host__ __device__ __forceinline__ void wino_output_tile(const WinoOutParams& p, int b, int ty, int tx, int c, float2 bv,
+                                                          float& sum0, float& sum1, float& sq0, float& sq1) {
+  const float inv = 1.0f / WINO_WSCALE;
+  const int64_t m = ((int64_t)b * p.th + ty) * p.tw + tx;
+  float mx[36], my[36];
+#pragma unroll
+  for (int q = 0; q < 36; ++q) {
+    const float2 v = *reinterpret_cast<const float2*>(p.m + ((int64_t)q * p.Mtot + m) * p.Cout + c);
+    mx[q] = v.x; my[q] = v.y;
+  }
+  // residual of the 4x4 output pixels (same / nearest-up / 2x2-average addressed)
+  constexpr int NRES = RES == BBDM_RES_NONE ? 1 : (RES == BBDM_RES_UP2 ? 4 : 16);
+  float2 rs[NRES];
+  if constexpr (RES == BBDM_RES_SAME) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        rs[i * 4 + j] = *reinterpret_cast<const float2*>(
+            p.residual + (((int64_t)b * p.H + 4 * ty + i) * p.W + 4 * tx + j) * p.Cout + c);
+  } else if constexpr (RES == BBDM_RES_UP2) {
+    // output pixels (4ty+i, 4tx+j) read source pixel (2ty + i/2, 2tx + j/2): 2x2 distinct values per tile
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        rs[i * 2 + j] = *reinterpret_cast<const float2*>(
+            p.residual + (((int64_t)b * (p.H >> 1) + 2 * ty + i) * (p.W >> 1) + 2 * tx + j) * p.Cout + c);
+  } else if constexpr (RES == BBDM_RES_DOWN2) {
+    const int64_t W2 = (int64_t)p.W * 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float* rp = p.residual + (((int64_t)b * p.H * 2 + (4 * ty + i) * 2) * W2 + (4 * tx + j) * 2) * p.Cout + c;
+        const float2 t0 = *reinterpret_cast<const float2*>(rp), t1 = *reinterpret_cast<const float2*>(rp + p.Cout);
+        const float2 t2 = *reinterpret_cast<const float2*>(rp + W2 * p.Cout);
+        const float2 t3 = *reinterpret_cast<const float2*>(rp + (W2 + 1) * p.Cout);
+        rs[i * 4 + j] = make_float2(0.25f * (((t0.x + t1.x) + t2.x) + t3.x), 0.25f * (((t0.y + t1.y) + t2.y) + t3.y));
+      }
+  }
+  // Y = A^T M A: columns (6 -> 4 rows), then rows (6 -> 4 columns)
+  float tx4[24], ty4[24], yx[16], yy[16];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) { wino_at6<6, 6>(mx + j, tx4 + j); wino_at6<6, 6>(my + j, ty4 + j); }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { wino_at6<1, 1>(tx4 + 6 * i, yx + 4 * i); wino_at6<1, 1>(ty4 + 6 * i, yy + 4 * i); }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int hh = 4 * ty + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ww = 4 * tx + j;
+      float r0 = fmaf(yx[i * 4 + j], inv, bv.x), r1 = fmaf(yy[i * 4 + j], inv, bv.y);
+      if constexpr (RES == BBDM_RES_SAME || RES == BBDM_RES_DOWN2) {
+        r0 += rs[i * 4 + j].x; r1 += rs[i * 4 + j].y;
+      } else if constexpr (RES == BBDM_RES_UP2) {
+        r0 += rs[(i >> 1) * 2 + (j >> 1)].x; r1 += rs[(i >> 1) * 2 + (j >> 1)].y;
+      }
+      *reinterpret_cast<float2*>(p.out + (((int64_t)b * p.H + hh) * p.W + ww) * p.Cout + c) = make_float2(r0, r1);
+      sum0 += r0; sum1 += r1;
+      sq0 = fmaf(r0, r0, sq0); sq1 = fmaf(r1, r1, sq1);
+    }
+  }
+}
+
 template <int RES>
 __global__ void __launch_bounds__(256, 2)
 wino_output_kernel(const WinoOutParams p) {
@@ -364,70 +433,7 @@ wino_output_kernel(const WinoOutParams p) {
   float2 bv = make_float2(0.f, 0.f);
   if (p.bias) bv = *reinterpret_cast<const float2*>(p.bias + c);
   float sum0 = 0.f, sum1 = 0.f, sq0 = 0.f, sq1 = 0.f;
-  const float inv = 1.0f / WINO_WSCALE;
-  for (int tx = tl; tx < p.tw; tx += 8) {
-    const int64_t m = ((int64_t)b * p.th + ty) * p.tw + tx;
-    float mx[36], my[36];
-#pragma unroll
-    for (int q = 0; q < 36; ++q) {
-      const float2 v = *reinterpret_cast<const float2*>(p.m + ((int64_t)q * p.Mtot + m) * p.Cout + c);
-      mx[q] = v.x; my[q] = v.y;
-    }
-    // residual of the 4x4 output pixels (same / nearest-up / 2x2-average addressed), same summation order as before
-    constexpr int NRES = RES == BBDM_RES_NONE ? 1 : (RES == BBDM_RES_UP2 ? 4 : 16);
-    float2 rs[NRES];
-    if constexpr (RES == BBDM_RES_SAME) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          rs[i * 4 + j] = *reinterpret_cast<const float2*>(
-              p.residual + (((int64_t)b * p.H + 4 * ty + i) * p.W + 4 * tx + j) * p.Cout + c);
-    } else if constexpr (RES == BBDM_RES_UP2) {
-      // output pixels (4ty+i, 4tx+j) read source pixel (2ty + i/2, 2tx + j/2): 2x2 distinct values per tile
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-          rs[i * 2 + j] = *reinterpret_cast<const float2*>(
-              p.residual + (((int64_t)b * (p.H >> 1) + 2 * ty + i) * (p.W >> 1) + 2 * tx + j) * p.Cout + c);
-    } else if constexpr (RES == BBDM_RES_DOWN2) {
-      const int64_t W2 = (int64_t)p.W * 2;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float* rp = p.residual + (((int64_t)b * p.H * 2 + (4 * ty + i) * 2) * W2 + (4 * tx + j) * 2) * p.Cout + c;
-          const float2 t0 = *reinterpret_cast<const float2*>(rp), t1 = *reinterpret_cast<const float2*>(rp + p.Cout);
-          const float2 t2 = *reinterpret_cast<const float2*>(rp + W2 * p.Cout);
-          const float2 t3 = *reinterpret_cast<const float2*>(rp + (W2 + 1) * p.Cout);
-          rs[i * 4 + j] = make_float2(0.25f * (((t0.x + t1.x) + t2.x) + t3.x), 0.25f * (((t0.y + t1.y) + t2.y) + t3.y));
-        }
-    }
-    // Y = A^T M A: columns (6 -> 4 rows), then rows (6 -> 4 columns)
-    float tx4[24], ty4[24], yx[16], yy[16];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) { wino_at6<6, 6>(mx + j, tx4 + j); wino_at6<6, 6>(my + j, ty4 + j); }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { wino_at6<1, 1>(tx4 + 6 * i, yx + 4 * i); wino_at6<1, 1>(ty4 + 6 * i, yy + 4 * i); }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int hh = 4 * ty + i;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int ww = 4 * tx + j;
-        float r0 = fmaf(yx[i * 4 + j], inv, bv.x), r1 = fmaf(yy[i * 4 + j], inv, bv.y);
-        if constexpr (RES == BBDM_RES_SAME || RES == BBDM_RES_DOWN2) {
-          r0 += rs[i * 4 + j].x; r1 += rs[i * 4 + j].y;
-        } else if constexpr (RES == BBDM_RES_UP2) {
-          r0 += rs[(i >> 1) * 2 + (j >> 1)].x; r1 += rs[(i >> 1) * 2 + (j >> 1)].y;
-        }
-        *reinterpret_cast<float2*>(p.out + (((int64_t)b * p.H + hh) * p.W + ww) * p.Cout + c) = make_float2(r0, r1);
-        sum0 += r0; sum1 += r1;
-        sq0 = fmaf(r0, r0, sq0); sq1 = fmaf(r1, r1, sq1);
-      }
-    }
-  }
+  for (int tx = tl; tx < p.tw; tx += 8) wino_output_tile<RES>(p, b, ty, tx, c, bv, sum0, sum1, sq0, sq1);
   if (p.stats) {
     // fixed-order combine of the 8 tile-column lanes => deterministic partial sums
     red[tl][lane * 2][0] = sum0; red[tl][lane * 2][1] = sq0;
