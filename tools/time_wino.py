@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Time the Winograd transform kernels (and the position GEMM) in isolation for the cfg2 layer shapes.
-    python tools/time_wino.py [--once]        # --once: one launch per kernel (for ncu)"""
+    python tools/time_wino.py [--once]        # --once: one launch per kernel (for ncu)
+    python tools/time_wino.py --output-only   # only the output transform, without / with a same-size residual"""
 import json
 import sys
 import os
@@ -31,6 +32,21 @@ def main():
     be = cabi.CudaBackend()
     dev = "cuda"
     rows = []
+    if "--output-only" in sys.argv:
+        for B, H, W, Cout in ((16, 128, 128, 512), (16, 64, 64, 1024)):
+            th, tw, mt, ok = be.wino_geometry(B, H, W)
+            m = torch.randn((36, mt, Cout), device=dev)
+            out, res = torch.empty((B, H, W, Cout), device=dev), torch.randn((B, H, W, Cout), device=dev)
+            part = torch.empty((B * th, Cout, 2), device=dev)
+            t0 = timeit(lambda: be.wino_output(m, B=B, H=H, W=W, Cout=Cout, out=out, stats_partial=part), 10)
+            t1 = timeit(lambda: be.wino_output(m, B=B, H=H, W=W, Cout=Cout, out=out, stats_partial=part, residual=res,
+                                               res_mode=cabi.RES_SAME), 10)
+            gb = (36 * mt * Cout * 4 + B * H * W * Cout * 4) / 1e9
+            print(json.dumps({"B": B, "H": H, "W": W, "Cout": Cout, "tiles": mt, "wino_output_ms": t0,
+                              "wino_output_tbps": gb / t0, "wino_output_residual_ms": t1,
+                              "wino_output_residual_tbps": (gb + B * H * W * Cout * 4 / 1e9) / t1}))
+        be.check_fault()
+        return
     for B, H, W, Cin, Cout in (SHAPES[1:2] if once else SHAPES):
         x = torch.randn(B, H, W, Cin, device=dev)
         mean, rstd = torch.zeros(B, 32, device=dev), torch.ones(B, 32, device=dev)
